@@ -1,0 +1,117 @@
+"""ctypes binding of libmg2d_sm100.so (C ABI: include/mg2d.h).
+
+There is NO fallback: if the shared library is missing, does not load, or the device is not sm_100, every
+entry point raises.  PyTorch is used only for device memory, streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmg2d_sm100.so")
+
+C128, C64 = 0, 1
+MODE_APPLY, MODE_RESID = 0, 1
+DOT_OUT2, DOT_OUTIN_RE, DOT_OUTIN_IM, DOT_B2, NDOTS = 0, 1, 2, 3, 4
+
+_vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+
+# name -> argtypes (after the leading mg2d_ctx*); mirrors include/mg2d.h one to one
+SIGNATURES = {
+    "mg2d_wilson_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp],
+    "mg2d_lvl0_matrix": [_vp, _vp, _vp, _d, _i, _i, _i, _i, _vp],
+    "mg2d_stencil_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp, _vp],
+    "mg2d_block_inverse": [_vp, _vp, _i, _ll, _i, _vp],
+    "mg2d_relax_jacobi": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _vp],
+    "mg2d_relax_gs": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp],
+    "mg2d_mr_update": [_vp, _vp, _vp, _vp, _d, _ll, _i, _i, _ll, _vp],
+    "mg2d_axpy": [_vp, _vp, _d, _d, _vp, _ll, _i, _vp],
+    "mg2d_zero": [_vp, _ll, _i, _vp],
+    "mg2d_copy": [_vp, _vp, _ll, _i, _vp],
+    "mg2d_convert": [_vp, _i, _vp, _i, _ll, _vp],
+    "mg2d_norm2": [_vp, _ll, _i, _vp, _vp],
+    "mg2d_cdot_batch": [_vp, _ll, _i, _vp, _ll, _i, _ll, _i, _vp, _vp],
+    "mg2d_scale_inv_norm": [_vp, _vp, _ll, _i, _vp],
+    "mg2d_restrict": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mg2d_prolong_add": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mg2d_pack_null": [_vp, _vp, _i, _ll, _i, _i, _ll, _i, _i, _vp],
+    "mg2d_norm_nn": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mg2d_ortho": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "mg2d_check_ortho": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "mg2d_coarse_matrix": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mg2d_minres_solve": [_vp, _vp, _i, _vp, _vp],
+    "mg2d_scale_phi": [_vp, _vp, _ll, _vp, _i, _ll, _i, _vp],
+    "mg2d_s2_relax": [_vp, _vp, _i, _d, _d, _i, _i, _vp],
+    "mg2d_s2_project": [_vp, _vp, _vp, _i, _d, _d, _i, _vp],
+    "mg2d_s2_interpolate": [_vp, _vp, _i, _i, _vp],
+    "mg2d_s2_residue_mag": [_vp, _vp, _i, _d, _d, _vp, _vp],
+    "mg2d_s2_scale": [_vp, _d, _ll, _vp],
+}
+PLAIN = {  # entry points without the uniform (ctx, ...) -> int shape
+    "mg2d_version": ([], _i),
+    "mg2d_create": ([C.POINTER(_vp), _i], _i),
+    "mg2d_destroy": ([_vp], _i),
+    "mg2d_last_error": ([_vp], C.c_char_p),
+    "mg2d_launch_count": ([_vp], _i),
+}
+
+_lib = None
+
+
+class MG2DError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises MG2DError when it is absent -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MG2DError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C 2d_multigrid_b200/csrc).  This package has no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (args, res) in PLAIN.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, res
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = [_vp] + args, _i
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One mg2d_ctx per GPU / stream of work (mg2d_create / mg2d_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.mg2d_create(C.byref(h), device)
+        if rc != 0:
+            raise MG2DError(f"mg2d_create(device={device}) failed with code {rc} "
+                            "(needs a CUDA device of compute capability 10.x; no fallback exists)")
+        self.h = h
+        self.device = device
+
+    def call(self, name: str, *args):
+        rc = getattr(self.lib, name)(self.h, *args)
+        if rc != 0:
+            raise MG2DError(f"{name} failed ({rc}): {self.lib.mg2d_last_error(self.h).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.mg2d_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mg2d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,346 @@
+// blas.cu -- handle management and the fused vector updates of the MR smoother / V-cycle driver.
+//   mg2d_mr_update       MR smoother step (ours; BASELINE.json north_star)
+//   mg2d_norm2 / scale   f_g_norm, S6/modules_indiv.h:70-92
+//   mg2d_cdot_batch      Gram matrix + source of f_min_res, S6/modules_main.h:324-366
+//   mg2d_scale_phi       f_scale_phi, S6/modules_main.h:375-384
+//   mg2d_minres_solve    A.colPivHouseholderQr().solve(src), S6/modules_main.h:371
+// All are pure streaming kernels: HBM-bound, 16-byte (c128) / 8-byte (c64) vector accesses, grid-stride.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BL_THREADS = 256;
+
+inline int stream_grid(mg2d_ctx* ctx, long long n, int per_thread = 1) {
+    long long nb = (n + (long long)BL_THREADS * per_thread - 1) / ((long long)BL_THREADS * per_thread);
+    long long cap = (long long)ctx->num_sms * 8;
+    if (nb > cap) nb = cap;
+    if (nb > MG2D_MAX_PARTIALS) nb = MG2D_MAX_PARTIALS;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+mr_update_kernel(cplx<T>* __restrict__ phi, cplx<T>* __restrict__ res, const cplx<T>* __restrict__ t,
+                 const double* __restrict__ dots, double omega, long long n, long long vstride) {
+    using C = cplx<T>;
+    const int v = blockIdx.y;
+    const double tt = dots[4 * v + MG2D_DOT_OUT2];
+    // alpha = omega * <t,res>/<t,t>
+    const double ar = tt > 0.0 ? omega * dots[4 * v + MG2D_DOT_OUTIN_RE] / tt : 0.0;
+    const double ai = tt > 0.0 ? omega * dots[4 * v + MG2D_DOT_OUTIN_IM] / tt : 0.0;
+    const C alpha = mk<T>((T)ar, (T)ai), nalpha = mk<T>((T)-ar, (T)-ai);
+    phi += (size_t)v * vstride; res += (size_t)v * vstride; t += (size_t)v * vstride;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C p = phi[e], r = res[e];
+        const C tv = __ldg(t + e);
+        cfma(p, alpha, r);
+        cfma(r, nalpha, tv);
+        phi[e] = p; res[e] = r;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+axpy_kernel(cplx<T>* __restrict__ y, const cplx<T>* __restrict__ x, double a_re, double a_im,
+            const double* __restrict__ a_dev, long long n) {
+    using C = cplx<T>;
+    if (a_dev) { a_re = a_dev[0]; a_im = a_dev[1]; }
+    const C a = mk<T>((T)a_re, (T)a_im);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C yv = y[e];
+        cfma(yv, a, __ldg(x + e));
+        y[e] = yv;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS) zero_kernel(cplx<T>* __restrict__ x, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        x[e] = mk<T>(0, 0);
+}
+
+template <typename TD, typename TS>
+__global__ void __launch_bounds__(BL_THREADS) convert_kernel(cplx<TD>* __restrict__ dst, const cplx<TS>* __restrict__ src, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const cplx<TS> s = __ldg(src + e);
+        dst[e] = mk<TD>((TD)s.x, (TD)s.y);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+norm2_kernel(const cplx<T>* __restrict__ x, long long n, double* __restrict__ partials, unsigned int* __restrict__ counter,
+             double* __restrict__ out) {
+    double red[1] = {0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const cplx<T> v = __ldg(x + e);
+        red[0] += (double)v.x * v.x + (double)v.y * v.y;
+    }
+    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+}
+
+// one (i,j) pair per blockIdx.y; out[2*(i*ny+j)] = sum conj(x_i) y_j
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+cdot_kernel(const cplx<T>* __restrict__ x, long long xstride, const cplx<T>* __restrict__ y, long long ystride, int ny,
+            long long n, double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out) {
+    const int pair = blockIdx.y;
+    const int i = pair / ny, j = pair - i * ny;
+    const cplx<T>* xi = x + (size_t)i * xstride;
+    const cplx<T>* yj = y + (size_t)j * ystride;
+    double red[2] = {0.0, 0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const cplx<T> a = __ldg(xi + e), b = __ldg(yj + e);
+        red[0] += (double)a.x * b.x + (double)a.y * b.y;
+        red[1] += (double)a.x * b.y - (double)a.y * b.x;
+    }
+    grid_reduce<2, BL_THREADS>(red, partials + (size_t)pair * MG2D_MAX_PARTIALS * 2, counter + pair, out + 2 * pair,
+                               blockIdx.x, gridDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+scale_inv_norm_kernel(cplx<T>* __restrict__ x, const double* __restrict__ norm2, long long n) {
+    const double inv = 1.0 / sqrt(norm2[0]);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        cplx<T> v = x[e];
+        // the reference divides (vec /= g_norm, S6/modules_indiv.h:89); keep a true division in fp64
+        if constexpr (sizeof(T) == 8) { const double nrm = sqrt(norm2[0]); v.x /= nrm; v.y /= nrm; }
+        else { v.x = (T)(v.x * inv); v.y = (T)(v.y * inv); }
+        x[e] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+scale_phi_kernel(cplx<T>* __restrict__ phi, cplx<T>* __restrict__ e, long long estride, const double* __restrict__ a,
+                 int ncopies, long long n) {
+    using C = cplx<T>;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        C p = phi[k];
+        for (int q = 0; q < ncopies; ++q) {
+            C* eq = e + (size_t)q * estride;
+            cfma(p, mk<T>((T)a[2 * q], (T)a[2 * q + 1]), eq[k]);
+            eq[k] = mk<T>(0, 0);
+        }
+        phi[k] = p;
+    }
+}
+
+// column-pivoted Householder QR solve of an n x n (n <= 4) complex system, one thread.
+__global__ void minres_solve_kernel(const double* __restrict__ gram, const double* __restrict__ src, int n,
+                                    double* __restrict__ a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double2 A[4][4], c[4], y[4];
+    int perm[4];
+    double diag[4];
+    for (int i = 0; i < n; ++i) {
+        perm[i] = i; c[i] = make_double2(src[2 * i], src[2 * i + 1]);
+        for (int j = 0; j < n; ++j) A[i][j] = make_double2(gram[2 * (i * n + j)], gram[2 * (i * n + j) + 1]);
+    }
+    for (int k = 0; k < n; ++k) {
+        int best = k; double bn = -1.0;
+        for (int j = k; j < n; ++j) {
+            double s = 0.0;
+            for (int i = k; i < n; ++i) s += A[i][j].x * A[i][j].x + A[i][j].y * A[i][j].y;
+            if (s > bn) { bn = s; best = j; }
+        }
+        if (best != k) {
+            for (int i = 0; i < n; ++i) { double2 t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; }
+            int t = perm[k]; perm[k] = perm[best]; perm[best] = t;
+        }
+        double alpha = 0.0;
+        for (int i = k; i < n; ++i) alpha += A[i][k].x * A[i][k].x + A[i][k].y * A[i][k].y;
+        alpha = sqrt(alpha);
+        if (alpha == 0.0) { diag[k] = 0.0; continue; }
+        double2 v[4];
+        for (int i = k; i < n; ++i) v[i] = A[i][k];
+        const double a0 = sqrt(v[k].x * v[k].x + v[k].y * v[k].y);
+        double2 ph = a0 != 0.0 ? make_double2(v[k].x / a0, v[k].y / a0) : make_double2(1.0, 0.0);
+        v[k].x += ph.x * alpha; v[k].y += ph.y * alpha;
+        double vn = 0.0;
+        for (int i = k; i < n; ++i) vn += v[i].x * v[i].x + v[i].y * v[i].y;
+        vn = sqrt(vn);
+        for (int i = k; i < n; ++i) { v[i].x /= vn; v[i].y /= vn; }
+        for (int j = k; j < n; ++j) {            // A[k:,j] -= 2 v (v^H A[k:,j])
+            double2 d = make_double2(0.0, 0.0);
+            for (int i = k; i < n; ++i) cfmac(d, v[i], A[i][j]);
+            for (int i = k; i < n; ++i) { double2 t = cmul(v[i], d); A[i][j].x -= 2.0 * t.x; A[i][j].y -= 2.0 * t.y; }
+        }
+        double2 d = make_double2(0.0, 0.0);
+        for (int i = k; i < n; ++i) cfmac(d, v[i], c[i]);
+        for (int i = k; i < n; ++i) { double2 t = cmul(v[i], d); c[i].x -= 2.0 * t.x; c[i].y -= 2.0 * t.y; }
+        diag[k] = sqrt(A[k][k].x * A[k][k].x + A[k][k].y * A[k][k].y);
+    }
+    double dmax = 0.0;
+    for (int k = 0; k < n; ++k) dmax = fmax(dmax, diag[k]);
+    const double thresh = 2.220446049250313e-16 * n * dmax;
+    int rank = 0;
+    for (int k = 0; k < n; ++k) rank += diag[k] > thresh ? 1 : 0;
+    for (int i = 0; i < n; ++i) y[i] = make_double2(0.0, 0.0);
+    for (int i = rank - 1; i >= 0; --i) {
+        double2 s = c[i];
+        for (int j = i + 1; j < rank; ++j) { double2 t = cmul(A[i][j], y[j]); s.x -= t.x; s.y -= t.y; }
+        const double den = A[i][i].x * A[i][i].x + A[i][i].y * A[i][i].y;
+        y[i] = make_double2((s.x * A[i][i].x + s.y * A[i][i].y) / den, (s.y * A[i][i].x - s.x * A[i][i].y) / den);
+    }
+    for (int i = 0; i < n; ++i) { a[2 * perm[i]] = y[i].x; a[2 * perm[i] + 1] = y[i].y; }
+}
+
+}  // namespace
+
+// ---- handle ----------------------------------------------------------------------------------------------
+extern "C" int mg2d_version(void) { return 100; }
+
+extern "C" int mg2d_create(mg2d_ctx** out, int device) {
+    if (!out) return MG2D_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MG2D_ECUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return MG2D_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MG2D_ECUDA;
+    if (prop.major != 10) return MG2D_EUNSUPPORTED;   // sm_100a only: no fallback path exists
+    mg2d_ctx* c = new mg2d_ctx();
+    c->device = device; c->launches = 0; c->num_sms = prop.multiProcessorCount; c->err[0] = 0;
+    c->partials = nullptr; c->counter = nullptr; c->status = nullptr;
+    if (cudaMalloc(&c->partials, sizeof(double) * MG2D_MAX_PARTIALS * 4 * 64) != cudaSuccess ||
+        cudaMalloc(&c->counter, sizeof(unsigned int) * 256) != cudaSuccess ||
+        cudaMalloc(&c->status, sizeof(int) * 16) != cudaSuccess ||
+        cudaMemset(c->counter, 0, sizeof(unsigned int) * 256) != cudaSuccess ||
+        cudaMemset(c->status, 0, sizeof(int) * 16) != cudaSuccess) {
+        cudaFree(c->partials); cudaFree(c->counter); cudaFree(c->status); delete c;
+        return MG2D_ECUDA;
+    }
+    *out = c;
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_destroy(mg2d_ctx* c) {
+    if (!c) return MG2D_EINVAL;
+    cudaSetDevice(c->device);
+    cudaFree(c->partials); cudaFree(c->counter); cudaFree(c->status);
+    delete c;
+    return MG2D_OK;
+}
+
+extern "C" const char* mg2d_last_error(mg2d_ctx* c) { return c ? c->err : "mg2d: null handle"; }
+extern "C" int mg2d_launch_count(mg2d_ctx* c) { return c ? c->launches : -1; }
+
+#define DISPATCH_T(dtype, CALL_D, CALL_F, NAME)                                         \
+    if (dtype == MG2D_C128) { CALL_D; } else if (dtype == MG2D_C64) { CALL_F; }         \
+    else return mg2d_fail(ctx, MG2D_EINVAL, NAME ": bad dtype");                        \
+    return mg2d_check_launch(ctx, NAME)
+
+extern "C" int mg2d_mr_update(mg2d_ctx* ctx, void* phi, void* res, const void* t, const double* dots, double omega,
+                              long long nelem, int dtype, int nvec, long long vstride, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !res || !t || !dots || nelem < 1 || nvec < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_mr_update: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(stream_grid(ctx, nelem), nvec);
+    DISPATCH_T(dtype,
+        (mr_update_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)phi, (double2*)res, (const double2*)t, dots, omega, nelem, vstride)),
+        (mr_update_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)phi, (float2*)res, (const float2*)t, dots, omega, nelem, vstride)),
+        "mg2d_mr_update");
+}
+
+extern "C" int mg2d_axpy(mg2d_ctx* ctx, void* y, const void* x, double a_re, double a_im, const double* a_dev,
+                         long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!y || !x || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_axpy: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (axpy_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)y, (const double2*)x, a_re, a_im, a_dev, nelem)),
+        (axpy_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)y, (const float2*)x, a_re, a_im, a_dev, nelem)),
+        "mg2d_axpy");
+}
+
+extern "C" int mg2d_zero(mg2d_ctx* ctx, void* x, long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_zero: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (zero_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, nelem)),
+        (zero_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, nelem)),
+        "mg2d_zero");
+}
+
+extern "C" int mg2d_copy(mg2d_ctx* ctx, void* dst, const void* src, long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!dst || !src || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_copy: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (convert_kernel<double, double><<<grid, BL_THREADS, 0, st>>>((double2*)dst, (const double2*)src, nelem)),
+        (convert_kernel<float, float><<<grid, BL_THREADS, 0, st>>>((float2*)dst, (const float2*)src, nelem)),
+        "mg2d_copy");
+}
+
+extern "C" int mg2d_convert(mg2d_ctx* ctx, void* dst, int dst_dtype, const void* src, int src_dtype, long long nelem, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!dst || !src || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_convert: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    if (dst_dtype == MG2D_C128 && src_dtype == MG2D_C64) convert_kernel<double, float><<<grid, BL_THREADS, 0, st>>>((double2*)dst, (const float2*)src, nelem);
+    else if (dst_dtype == MG2D_C64 && src_dtype == MG2D_C128) convert_kernel<float, double><<<grid, BL_THREADS, 0, st>>>((float2*)dst, (const double2*)src, nelem);
+    else if (dst_dtype == src_dtype) return mg2d_copy(ctx, dst, src, nelem, dst_dtype, stream);
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_convert: bad dtype");
+    return mg2d_check_launch(ctx, "mg2d_convert");
+}
+
+extern "C" int mg2d_norm2(mg2d_ctx* ctx, const void* x, long long nelem, int dtype, double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || !out || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_norm2: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (norm2_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)x, nelem, ctx->partials, ctx->counter, out)),
+        (norm2_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)x, nelem, ctx->partials, ctx->counter, out)),
+        "mg2d_norm2");
+}
+
+extern "C" int mg2d_cdot_batch(mg2d_ctx* ctx, const void* x, long long xstride, int nx, const void* y, long long ystride,
+                               int ny, long long nelem, int dtype, double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || !y || !out || nelem < 1 || nx < 1 || ny < 1 || nx * ny > 64) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_cdot_batch: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(stream_grid(ctx, nelem), nx * ny);
+    DISPATCH_T(dtype,
+        (cdot_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)x, xstride, (const double2*)y, ystride, ny, nelem, ctx->partials, ctx->counter, out)),
+        (cdot_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)x, xstride, (const float2*)y, ystride, ny, nelem, ctx->partials, ctx->counter, out)),
+        "mg2d_cdot_batch");
+}
+
+extern "C" int mg2d_scale_inv_norm(mg2d_ctx* ctx, void* x, const double* norm2, long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || !norm2 || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_scale_inv_norm: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (scale_inv_norm_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, norm2, nelem)),
+        (scale_inv_norm_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, norm2, nelem)),
+        "mg2d_scale_inv_norm");
+}
+
+extern "C" int mg2d_minres_solve(mg2d_ctx* ctx, const double* gram, const double* src, int ncopies, double* a, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!gram || !src || !a || ncopies < 1 || ncopies > 4) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_minres_solve: bad argument");
+    minres_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gram, src, ncopies, a);
+    return mg2d_check_launch(ctx, "mg2d_minres_solve");
+}
+
+extern "C" int mg2d_scale_phi(mg2d_ctx* ctx, void* phi, void* e, long long estride, const double* a, int ncopies,
+                              long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !e || !a || ncopies < 1 || ncopies > 4 || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_scale_phi: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (scale_phi_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)phi, (double2*)e, estride, a, ncopies, nelem)),
+        (scale_phi_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)phi, (float2*)e, estride, a, ncopies, nelem)),
+        "mg2d_scale_phi");
+}

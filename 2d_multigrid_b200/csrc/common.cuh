@@ -1,0 +1,126 @@
+// common.cuh -- shared device helpers for libmg2d_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/mg2d.h"
+
+#define MG2D_MAX_PARTIALS 4096   // max CTAs contributing to one reduction
+#define MG2D_MAX_RED 64          // max doubles per reduction (batched dots)
+
+struct mg2d_ctx {
+    int device;
+    int launches;
+    double* partials;        // [MG2D_MAX_PARTIALS][MG2D_MAX_RED]
+    unsigned int* counter;   // last-block-done tickets, one per reduction "channel"
+    int* status;
+    int num_sms;
+    char err[512];
+};
+
+static inline int mg2d_fail(mg2d_ctx* c, int code, const char* msg) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s", msg);
+    return code;
+}
+static inline int mg2d_check_launch(mg2d_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+        return MG2D_ECUDA;
+    }
+    if (c) c->launches++;
+    return MG2D_OK;
+}
+
+// ---- complex arithmetic on (re,im) pairs ------------------------------------------------------------
+template <typename T> struct cplx_of;
+template <> struct cplx_of<double> { using type = double2; };
+template <> struct cplx_of<float>  { using type = float2; };
+template <typename T> using cplx = typename cplx_of<T>::type;
+
+template <typename T> __device__ __forceinline__ cplx<T> mk(T re, T im) { cplx<T> r; r.x = re; r.y = im; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+// conj(a) * b
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) { C r; r.x = a.x * b.x + a.y * b.y; r.y = a.x * b.y - a.y * b.x; return r; }
+// acc += a * b
+template <typename C> __device__ __forceinline__ void cfma(C& acc, C a, C b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+template <typename C> __device__ __forceinline__ void cfmac(C& acc, C a, C b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
+template <typename C> __device__ __forceinline__ C cmul_i(C a) { C r; r.x = -a.y; r.y = a.x; return r; }   // i*a
+template <typename C> __device__ __forceinline__ C cmul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }  // -i*a
+template <typename C, typename T> __device__ __forceinline__ C cscale(C a, T s) { a.x *= s; a.y *= s; return a; }
+
+// read-only 8/16-byte loads
+__device__ __forceinline__ double2 ldg(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ float2  ldg(const float2* p)  { return __ldg(p); }
+
+// 256-bit global accesses (sm_100a: LDG.E.256 / STG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ld256(const double2* p, double2& a, double2& b) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st256(double2* p, const double2& a, const double2& b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <typename C> __device__ __forceinline__ C shfl_xor_c(C v, int m) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, m); v.y = __shfl_xor_sync(0xffffffffu, v.y, m); return v;
+}
+template <typename C> __device__ __forceinline__ C shfl_c(C v, int src, int width = 32) {
+    v.x = __shfl_sync(0xffffffffu, v.x, src, width); v.y = __shfl_sync(0xffffffffu, v.y, src, width); return v;
+}
+
+// ---- deterministic grid-wide reduction of NR doubles -------------------------------------------------
+// Every CTA calls this with its per-thread values; the warp/CTA tree and the final pass over the per-CTA
+// partials run in a fixed order, so results are bit-reproducible for a fixed launch configuration.
+// `out[r]` is written by the last CTA to finish.  All threads of the CTA must call it.
+template <int NR, int NTHREADS>
+__device__ __forceinline__ void grid_reduce(double (&v)[NR], double* __restrict__ partials,
+                                            unsigned int* __restrict__ counter, double* __restrict__ out,
+                                            int cta_linear, int num_ctas) {
+    __shared__ double s_red[NR][NTHREADS / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double x = v[r];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+        if (lane == 0) s_red[r][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        double x = 0.0;
+        for (int w = 0; w < NTHREADS / 32; ++w) x += s_red[threadIdx.x][w];
+        partials[(size_t)cta_linear * NR + threadIdx.x] = x;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == (unsigned int)num_ctas - 1u);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // fixed-order sum over CTAs: warp r handles slot r (strided, then shuffle tree)
+        for (int r = warp; r < NR; r += NTHREADS / 32) {
+            double x = 0.0;
+            for (int c = lane; c < num_ctas; c += 32) x += __ldcg(&partials[(size_t)c * NR + r]);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+            if (lane == 0) out[r] = x;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}

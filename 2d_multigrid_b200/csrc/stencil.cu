@@ -1,0 +1,366 @@
+// stencil.cu -- generic 5-point block stencil with n x n complex blocks per site and slot.
+//
+// Replaces, for every level whose operator is stored (all coarse levels; level 0 in reference-compat mode):
+//   Level::f_apply_D   S6/level.h:251-265     v'(s) = D1 v(s+x) + D2 v(s-x) + D3 v(s+y) + D4 v(s-y) + D0 v(s)
+//   Level::f_residue   S6/level.h:61-77       r' = r - D phi           (+ norms of f_get_residue_mag :79-98)
+//   Level::f_relax     S6/level.h:100-128     phi(s) = -D0(s)^-1 (sum_{k>=1} D_k phi(s+d_k) - r(s))
+//                                             gs_flag=0 Jacobi ; gs_flag=1 lexicographic GS (x outer, y inner)
+//
+// Layout: D[s][k][j][i] (column-major blocks).  A group of G lanes owns one site and streams its 5*n*n
+// elements with stride G (element e = g + G*t), so a warp always reads 32 consecutive 16-byte elements:
+// lane g keeps row i = g % n and column-part jp = g / n; partial sums are combined with log2(G/n) butterfly
+// shuffles.  Algorithmic traffic per site (c128): apply (5n^2+2n)*16 B, relax (5n^2+3n)*16 B (+n^2*16 D0inv).
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+template <int N> struct GroupOf { static constexpr int G = (N == 1) ? 1 : (N == 2) ? 4 : (N == 4) ? 16 : 32; };
+
+// neighbour row pointer + site for slot k (1..4) of site (x,y) of an Lx x Ly strip with halo rows lo/hi
+template <typename C>
+__device__ __forceinline__ const C* nbr_ptr(const C* in, const C* lo, const C* hi, int k, int x, int y, int Lx, int Ly, int N) {
+    switch (k) {
+        case 0: return in + ((size_t)y * Lx + x) * N;
+        case 1: return in + ((size_t)y * Lx + ((x + 1 == Lx) ? 0 : x + 1)) * N;
+        case 2: return in + ((size_t)y * Lx + ((x == 0) ? Lx - 1 : x - 1)) * N;
+        case 3: return (y + 1 == Ly) ? hi + (size_t)x * N : in + ((size_t)(y + 1) * Lx + x) * N;
+        default: return (y == 0) ? lo + (size_t)x * N : in + ((size_t)(y - 1) * Lx + x) * N;
+    }
+}
+
+// sum_{k=K0..4} D_k(s) v(s+d_k), row i of the result valid in every lane of the group.
+// LD selects the load used for the field (ldcg for in-place Gauss-Seidel, ldg otherwise).
+template <typename T, int N, int G, int K0, bool COHERENT>
+__device__ __forceinline__ cplx<T> stencil_row(const cplx<T>* __restrict__ Ds, const cplx<T>* in, const cplx<T>* lo,
+                                               const cplx<T>* hi, int x, int y, int Lx, int Ly, int g) {
+    using C = cplx<T>;
+    constexpr int JP = G / N;                 // column parts per group
+    constexpr int ITERS = (5 * N) / JP;       // (k,j) pairs per lane
+    constexpr int T0 = (K0 * N) / JP;
+    const int jp = g / N;
+    C acc = mk<T>(0, 0);
+#pragma unroll
+    for (int t = T0; t < ITERS; ++t) {
+        const int k = (JP * t) / N;                 // compile-time after unrolling (jp < JP, JP | N)
+        const int j = jp + (JP * t) % N;
+        const C d = __ldg(Ds + g + G * t);
+        const C* p = nbr_ptr<C>(in, lo, hi, k, x, y, Lx, Ly, N) + j;
+        C v;
+        if (COHERENT) { v = __ldcg(p); } else { v = __ldg(p); }
+        cfma(acc, d, v);
+    }
+#pragma unroll
+    for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
+    return acc;
+}
+
+// out_i = - sum_j Dinv[j*N+i] w_j, w distributed one row per lane (lane i of the group holds w_i)
+template <typename T, int N, int G>
+__device__ __forceinline__ cplx<T> apply_minus_inv(const cplx<T>* __restrict__ Dinv_s, cplx<T> w, int g) {
+    using C = cplx<T>;
+    constexpr int JP = G / N;
+    const int i = g % N, jp = g / N;
+    C acc = mk<T>(0, 0);
+#pragma unroll
+    for (int u = 0; u < N / JP + (N % JP ? 1 : 0); ++u) {
+        const int j = jp + JP * u;
+        C wj = shfl_c(w, (j < N) ? j : 0, G);
+        if (j < N) { const C d = __ldg(Dinv_s + j * N + i); cfma(acc, d, wj); }
+    }
+#pragma unroll
+    for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
+    acc.x = -acc.x; acc.y = -acc.y;
+    return acc;
+}
+
+constexpr int ST_THREADS = 256;
+
+// MODE 0 apply, 1 residual, 2 Jacobi sweep
+template <typename T, int N, int MODE, bool DOTS>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in, const cplx<T>* __restrict__ in_lo,
+               const cplx<T>* __restrict__ in_hi, const cplx<T>* __restrict__ D, const cplx<T>* __restrict__ Dinv,
+               const cplx<T>* __restrict__ b, int Lx, int Ly, long long vstride, long long hstride,
+               double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ dots) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const int v = blockIdx.y;
+    out += (size_t)v * vstride; in += (size_t)v * vstride;
+    in_lo += (size_t)v * hstride; in_hi += (size_t)v * hstride;
+    if (b) b += (size_t)v * vstride;
+    const long long S = (long long)Lx * Ly;
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long nsteps = (S + GPB - 1) / GPB;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long s = step * GPB + grp;
+        const bool active = s < S;
+        if (!active) s = S - 1;
+        const int y = (int)(s / Lx), x = (int)(s - (long long)y * Lx);
+        const C* Ds = D + (size_t)s * 5 * N * N;
+        C o;
+        if (MODE == 2) {
+            C acc = stencil_row<T, N, G, 1, false>(Ds, in, in_lo, in_hi, x, y, Lx, Ly, g);
+            if (b) acc = csub(acc, __ldg(b + (size_t)s * N + i));
+            o = apply_minus_inv<T, N, G>(Dinv + (size_t)s * N * N, acc, g);
+        } else {
+            o = stencil_row<T, N, G, 0, false>(Ds, in, in_lo, in_hi, x, y, Lx, Ly, g);
+            if (MODE == 1) {
+                const C bb = __ldg(b + (size_t)s * N + i);
+                if (DOTS && active && jp == 0) red[3] += (double)bb.x * bb.x + (double)bb.y * bb.y;
+                o = csub(bb, o);
+            }
+        }
+        if (active && jp == 0) {
+            out[(size_t)s * N + i] = o;
+            if (DOTS) {
+                const C vi = __ldg(in + (size_t)s * N + i);
+                red[0] += (double)o.x * o.x + (double)o.y * o.y;
+                red[1] += (double)o.x * vi.x + (double)o.y * vi.y;
+                red[2] += (double)o.x * vi.y - (double)o.y * vi.x;
+            }
+        }
+    }
+    if (DOTS) grid_reduce<4, ST_THREADS>(red, partials + (size_t)v * MG2D_MAX_PARTIALS * 4, counter + v,
+                                         dots + 4 * v, blockIdx.x, gridDim.x);
+}
+
+// lexicographic Gauss-Seidel by anti-diagonal wavefronts (cooperative launch, grid.sync between fronts)
+template <typename T, int N>
+__global__ void __launch_bounds__(ST_THREADS)
+gs_wavefront_kernel(cplx<T>* phi, const cplx<T>* __restrict__ D, const cplx<T>* __restrict__ Dinv,
+                    const cplx<T>* __restrict__ r, int L, int num_iter, int nvec, long long vstride) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    cg::grid_group grid = cg::this_grid();
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const long long ngroups = (long long)gridDim.x * GPB;
+    const long long gid = (long long)blockIdx.x * GPB + grp;
+    for (int it = 0; it < num_iter; ++it) {
+        for (int c = 0; c <= 2 * L - 2; ++c) {
+            const int x0 = max(0, c - L + 1), x1 = min(c, L - 1);
+            const int cnt = x1 - x0 + 1;
+            const long long total = (long long)cnt * nvec;
+            const long long rounds = (total + ngroups - 1) / ngroups;
+            for (long long rd = 0; rd < rounds; ++rd) {
+                long long idx = rd * ngroups + gid;
+                const bool active = idx < total;
+                if (!active) idx = total - 1;
+                const int v = (int)(idx / cnt);
+                const int x = x0 + (int)(idx - (long long)v * cnt), y = c - x;
+                const size_t s = (size_t)y * L + x;
+                C* ph = phi + (size_t)v * vstride;
+                C acc = stencil_row<T, N, G, 1, true>(D + s * 5 * N * N, ph, ph + (size_t)(L - 1) * L * N, ph,
+                                                      x, y, L, L, g);
+                if (r) acc = csub(acc, __ldg(r + (size_t)v * vstride + s * N + i));
+                C o = apply_minus_inv<T, N, G>(Dinv + s * N * N, acc, g);
+                if (active && jp == 0) __stcg(ph + s * N + i, o);
+            }
+            grid.sync();
+        }
+    }
+}
+
+// D0inv[s] = inverse(D[s][0]); one warp per site, Gauss-Jordan with partial pivoting in shared memory
+template <typename T, int N>
+__global__ void block_inverse_kernel(cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ D, long long S) {
+    using C = cplx<T>;
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    C* A = reinterpret_cast<C*>(smem_raw) + (size_t)warp * 2 * N * N;   // A[i][j] row-major
+    C* B = A + N * N;
+    for (long long s = (long long)blockIdx.x * nwarps + warp; s < S; s += (long long)gridDim.x * nwarps) {
+        const C* src = D + (size_t)s * 5 * N * N;
+        for (int e = lane; e < N * N; e += 32) {
+            const int j = e / N, i = e - j * N;
+            A[i * N + j] = src[e];
+            B[i * N + j] = mk<T>(i == j ? (T)1 : (T)0, (T)0);
+        }
+        __syncwarp();
+        for (int c = 0; c < N; ++c) {
+            // pivot: largest |A[r][c]|, r >= c (ties -> smallest r)
+            T best = (T)-1; int br = c;
+            for (int r = c + lane; r < N; r += 32) {
+                const C a = A[r * N + c];
+                const T m = a.x * a.x + a.y * a.y;
+                if (m > best) { best = m; br = r; }
+            }
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const T ob = __shfl_xor_sync(0xffffffffu, best, m);
+                const int orr = __shfl_xor_sync(0xffffffffu, br, m);
+                if (ob > best || (ob == best && orr < br)) { best = ob; br = orr; }
+            }
+            if (br != c) {
+                for (int j = lane; j < N; j += 32) {
+                    C t = A[c * N + j]; A[c * N + j] = A[br * N + j]; A[br * N + j] = t;
+                    t = B[c * N + j]; B[c * N + j] = B[br * N + j]; B[br * N + j] = t;
+                }
+            }
+            __syncwarp();
+            const C pv = A[c * N + c];
+            const T den = pv.x * pv.x + pv.y * pv.y;
+            const C pinv = mk<T>(pv.x / den, -pv.y / den);
+            __syncwarp();
+            for (int j = lane; j < N; j += 32) {
+                A[c * N + j] = cmul(A[c * N + j], pinv);
+                B[c * N + j] = cmul(B[c * N + j], pinv);
+            }
+            __syncwarp();
+            for (int rr = 0; rr < N; ++rr) {
+                if (rr == c) continue;
+                const C f = A[rr * N + c];
+                __syncwarp();
+                for (int j = lane; j < N; j += 32) {
+                    C a = A[rr * N + j]; C t = cmul(f, A[c * N + j]); A[rr * N + j] = csub(a, t);
+                    C bb = B[rr * N + j]; t = cmul(f, B[c * N + j]); B[rr * N + j] = csub(bb, t);
+                }
+                __syncwarp();
+            }
+        }
+        C* dst = Dinv + (size_t)s * N * N;
+        for (int e = lane; e < N * N; e += 32) {
+            const int j = e / N, i = e - j * N;
+            dst[e] = B[i * N + j];
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, int N>
+int launch_stencil(mg2d_ctx* ctx, void* out, const void* in, const void* lo, const void* hi, const void* D,
+                   const void* Dinv, const void* b, int Lx, int Ly, int mode, int nvec, long long vstride,
+                   long long hstride, double* dots, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    const long long S = (long long)Lx * Ly;
+    long long nsteps = (S + GPB - 1) / GPB;
+    int gx = (int)(nsteps < MG2D_MAX_PARTIALS ? nsteps : MG2D_MAX_PARTIALS);
+    dim3 grid(gx, nvec);
+#define SL(MODE, DOTS)                                                                                         \
+    stencil_kernel<T, N, MODE, DOTS><<<grid, ST_THREADS, 0, st>>>((C*)out, (const C*)in, (const C*)lo, (const C*)hi, \
+        (const C*)D, (const C*)Dinv, (const C*)b, Lx, Ly, vstride, hstride, ctx->partials, ctx->counter, dots)
+    if (mode == 0) { if (dots) SL(0, true); else SL(0, false); }
+    else if (mode == 1) { if (dots) SL(1, true); else SL(1, false); }
+    else SL(2, false);
+#undef SL
+    return mg2d_check_launch(ctx, "mg2d_stencil");
+}
+
+template <typename T>
+int dispatch_stencil(mg2d_ctx* ctx, int n, void* out, const void* in, const void* lo, const void* hi, const void* D,
+                     const void* Dinv, const void* b, int Lx, int Ly, int mode, int nvec, long long vstride,
+                     long long hstride, double* dots, cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_stencil<T, N>(ctx, out, in, lo, hi, D, Dinv, b, Lx, Ly, mode, nvec, vstride, hstride, dots, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_stencil: n_dof must be one of 1,2,4,8,16,32");
+    }
+}
+
+template <typename T, int N>
+int launch_gs(mg2d_ctx* ctx, void* phi, const void* D, const void* Dinv, const void* r, int L, int num_iter,
+              int nvec, long long vstride, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_wavefront_kernel<T, N>, ST_THREADS, 0);
+    if (e != cudaSuccess || per_sm < 1) return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_relax_gs: occupancy query failed");
+    long long need = ((long long)L * nvec + GPB - 1) / GPB;
+    long long cap = (long long)per_sm * ctx->num_sms;
+    int grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    C* phi_ = (C*)phi; const C* D_ = (const C*)D; const C* Dinv_ = (const C*)Dinv; const C* r_ = (const C*)r;
+    void* args[] = {&phi_, &D_, &Dinv_, &r_, &L, &num_iter, &nvec, &vstride};
+    e = cudaLaunchCooperativeKernel((const void*)gs_wavefront_kernel<T, N>, dim3(grid), dim3(ST_THREADS), args, 0, st);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "mg2d_relax_gs: %s", cudaGetErrorString(e)); return MG2D_ECUDA; }
+    return mg2d_check_launch(ctx, "mg2d_relax_gs");
+}
+
+template <typename T>
+int dispatch_gs(mg2d_ctx* ctx, int n, void* phi, const void* D, const void* Dinv, const void* r, int L, int num_iter,
+                int nvec, long long vstride, cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_gs<T, N>(ctx, phi, D, Dinv, r, L, num_iter, nvec, vstride, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_gs: n_dof must be one of 1,2,4,8,16,32");
+    }
+}
+
+template <typename T, int N>
+int launch_inverse(mg2d_ctx* ctx, void* Dinv, const void* D, long long S, cudaStream_t st) {
+    using C = cplx<T>;
+    const size_t per_warp = 2 * (size_t)N * N * sizeof(C);
+    int warps = (int)(48 * 1024 / per_warp); if (warps > 8) warps = 8; if (warps < 1) warps = 1;
+    long long nb = (S + warps - 1) / warps; if (nb > ctx->num_sms * 16) nb = ctx->num_sms * 16;
+    block_inverse_kernel<T, N><<<(int)nb, warps * 32, warps * per_warp, st>>>((C*)Dinv, (const C*)D, S);
+    return mg2d_check_launch(ctx, "mg2d_block_inverse");
+}
+
+template <typename T>
+int dispatch_inverse(mg2d_ctx* ctx, int n, void* Dinv, const void* D, long long S, cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_inverse<T, N>(ctx, Dinv, D, S, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_block_inverse: n_dof must be one of 1,2,4,8,16,32");
+    }
+}
+
+}  // namespace
+
+extern "C" int mg2d_stencil_apply(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, const void* in_hi,
+                                  const void* D, const void* b, int n, int Lx, int Ly, int mode, int dtype,
+                                  int nvec, long long vstride, long long hstride, double* dots, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!out || !in || !in_lo || !in_hi || !D || Lx < 1 || Ly < 1 || nvec < 1 || nvec > 64)
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_stencil_apply: bad argument");
+    if (mode != MG2D_MODE_APPLY && mode != MG2D_MODE_RESID) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_stencil_apply: bad mode");
+    if (mode == MG2D_MODE_RESID && !b) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_stencil_apply: MODE_RESID needs b");
+    if (out == in) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_stencil_apply: out must not alias in");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_stencil<double>(ctx, n, out, in, in_lo, in_hi, D, nullptr, b, Lx, Ly, mode, nvec, vstride, hstride, dots, st);
+    if (dtype == MG2D_C64)  return dispatch_stencil<float>(ctx, n, out, in, in_lo, in_hi, D, nullptr, b, Lx, Ly, mode, nvec, vstride, hstride, dots, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_stencil_apply: bad dtype");
+}
+
+extern "C" int mg2d_relax_jacobi(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, const void* in_hi,
+                                 const void* D, const void* D0inv, const void* r, int n, int Lx, int Ly, int dtype,
+                                 int nvec, long long vstride, long long hstride, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!out || !in || !in_lo || !in_hi || !D || !D0inv || Lx < 1 || Ly < 1 || nvec < 1 || nvec > 64)
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_jacobi: bad argument");
+    if (out == in) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_jacobi: out must not alias in");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_stencil<double>(ctx, n, out, in, in_lo, in_hi, D, D0inv, r, Lx, Ly, 2, nvec, vstride, hstride, nullptr, st);
+    if (dtype == MG2D_C64)  return dispatch_stencil<float>(ctx, n, out, in, in_lo, in_hi, D, D0inv, r, Lx, Ly, 2, nvec, vstride, hstride, nullptr, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_jacobi: bad dtype");
+}
+
+extern "C" int mg2d_relax_gs(mg2d_ctx* ctx, void* phi, const void* D, const void* D0inv, const void* r, int n, int L,
+                             int num_iter, int dtype, int nvec, long long vstride, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !D || !D0inv || L < 2 || num_iter < 0 || nvec < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_gs: bad argument");
+    if (num_iter == 0) return MG2D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_gs<double>(ctx, n, phi, D, D0inv, r, L, num_iter, nvec, vstride, st);
+    if (dtype == MG2D_C64)  return dispatch_gs<float>(ctx, n, phi, D, D0inv, r, L, num_iter, nvec, vstride, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_gs: bad dtype");
+}
+
+extern "C" int mg2d_block_inverse(mg2d_ctx* ctx, void* D0inv, const void* D, int n, long long nsites, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!D0inv || !D || nsites < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_block_inverse: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_inverse<double>(ctx, n, D0inv, D, nsites, st);
+    if (dtype == MG2D_C64)  return dispatch_inverse<float>(ctx, n, D0inv, D, nsites, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_block_inverse: bad dtype");
+}

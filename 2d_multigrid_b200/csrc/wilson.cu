@@ -1,0 +1,217 @@
+// wilson.cu -- matrix-free U(1) Wilson-Dirac stencil on the fine lattice (n = 2 spin components).
+//
+// Replaces Level::f_compute_lvl0_matrix (wilson branch, S6/level.h:155-172) fused into Level::f_apply_D
+// (S6/level.h:251-265), f_residue (:61-77) and the two norms of f_get_residue_mag (:79-98):
+//
+//   (D psi)(s) = (2+m) psi(s) + U_x(s) 1/2(1-s1) psi(s+x) + conj(U_x(s-x)) 1/2(1+s1) psi(s-x)
+//                             + U_y(s) 1/2(1-s2) psi(s+y) + conj(U_y(s-y)) 1/2(1+s2) psi(s-y)
+//   1/2(1-s1)psi = 1/2 (a,-a),  a = psi0-psi1      1/2(1+s1)psi = 1/2 (b, b),  b = psi0+psi1
+//   1/2(1-s2)psi = 1/2 (c,-ic), c = psi0+i psi1    1/2(1+s2)psi = 1/2 (d, id), d = psi0-i psi1
+//
+// HBM roofline: algorithmic traffic 96 B/site in complex128 (psi in 32 + links 32 + out 32), +32 with b.
+//
+// Kernel design (v1, "column march"): a CTA owns a strip of WX consecutive x and marches over RY rows in y.
+// Each thread keeps the three rows psi(x,y-1), psi(x,y), psi(x,y+1) and U_y(x,y-1) in registers, so every
+// psi/U element is loaded from global memory exactly once per CTA (plus the two halo rows of the march and
+// two halo columns); x-neighbour data is exchanged as projected half-spinors (one complex each way) through
+// warp shuffles, with the warp-edge lanes falling back to a global load.
+#include "common.cuh"
+
+namespace {
+
+template <typename T> struct Spinor { cplx<T> c0, c1; };
+
+template <typename T>
+__device__ __forceinline__ Spinor<T> load_spinor(const cplx<T>* __restrict__ p, size_t s) {
+    Spinor<T> r;
+    if constexpr (sizeof(T) == 8) {
+        ld256(p + 2 * s, r.c0, r.c1);       // one LDG.E.256 per spinor (sm_100a)
+    } else {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p) + s);
+        r.c0 = make_float2(v.x, v.y); r.c1 = make_float2(v.z, v.w);
+    }
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ void store_spinor(cplx<T>* __restrict__ p, size_t s, const Spinor<T>& v) {
+    if constexpr (sizeof(T) == 8) {
+        st256(p + 2 * s, v.c0, v.c1);
+    } else {
+        reinterpret_cast<float4*>(p)[s] = make_float4(v.c0.x, v.c0.y, v.c1.x, v.c1.y);
+    }
+}
+
+constexpr int WX = 128;       // threads per CTA = x-extent of a CTA column strip
+constexpr int RY = 32;        // rows marched per work item
+
+// MODE 0: out = D in ; MODE 1: out = b - D in.  DOTS: also reduce |out|^2, <out,in>, |b|^2.
+template <typename T, int MODE, bool DOTS>
+__global__ void __launch_bounds__(WX)
+wilson_march_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in,
+                    const cplx<T>* __restrict__ in_lo, const cplx<T>* __restrict__ in_hi,
+                    const cplx<T>* __restrict__ U, const cplx<T>* __restrict__ U_lo,
+                    const cplx<T>* __restrict__ b, T diag, int Lx, int Ly,
+                    double* __restrict__ partials, unsigned int* __restrict__ counter,
+                    double* __restrict__ dots) {
+    using C = cplx<T>;
+    const int nsx = (Lx + WX - 1) / WX;
+    const int nsy = (Ly + RY - 1) / RY;
+    const int nwork = nsx * nsy;
+    const int lane = threadIdx.x & 31;
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    const T half = (T)0.5;
+
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int wy = w / nsx, wx = w - wy * nsx;
+        const int x = wx * WX + threadIdx.x;
+        const bool active = x < Lx;
+        const int xc = active ? x : Lx - 1;                  // clamp so that every lane takes part in shuffles
+        const int xp = (xc + 1 == Lx) ? 0 : xc + 1;
+        const int xm = (xc == 0) ? Lx - 1 : xc - 1;
+        const int y0 = wy * RY;
+        const int y1 = min(y0 + RY, Ly);
+
+        // rolling rows: prev = row y-1, cur = row y, next = row y+1
+        Spinor<T> prev = (y0 == 0) ? load_spinor<T>(in_lo, xc) : load_spinor<T>(in, (size_t)(y0 - 1) * Lx + xc);
+        Spinor<T> cur = load_spinor<T>(in, (size_t)y0 * Lx + xc);
+        C uy_prev = (y0 == 0) ? __ldg(U_lo + 2 * (size_t)xc + 1) : __ldg(U + 2 * ((size_t)(y0 - 1) * Lx + xc) + 1);
+
+        for (int y = y0; y < y1; ++y) {
+            const size_t s = (size_t)y * Lx + xc;
+            Spinor<T> next = (y + 1 == Ly) ? load_spinor<T>(in_hi, xc) : load_spinor<T>(in, s + Lx);
+            const Spinor<T> lk = load_spinor<T>(U, s);            // (U_x(s), U_y(s)) share the spinor layout
+            const C ux = lk.c0, uy = lk.c1;
+
+            // x-direction half spinors of THIS site, to be handed to the neighbours
+            C a_here = csub(cur.c0, cur.c1);                      // needed by site x-1  (their +x hop)
+            C wb_here = cmulc(ux, cadd(cur.c0, cur.c1));          // conj(U_x(s)) b(s): needed by site x+1
+            C a_xp = shfl_c(a_here, lane + 1);                    // a(s+x)
+            C wb_xm = shfl_c(wb_here, lane - 1);                  // conj(U_x(s-x)) b(s-x)
+            if (lane == 31 || xc + 1 == Lx) {                     // warp edge / periodic wrap: global load
+                Spinor<T> q = load_spinor<T>(in, (size_t)y * Lx + xp);
+                a_xp = csub(q.c0, q.c1);
+            }
+            if (lane == 0) {
+                Spinor<T> q = load_spinor<T>(in, (size_t)y * Lx + xm);
+                C uxm = __ldg(U + 2 * ((size_t)y * Lx + xm));
+                wb_xm = cmulc(uxm, cadd(q.c0, q.c1));
+            }
+            const C A = cmul(ux, a_xp);
+            const C B = wb_xm;
+            const C Cc = cmul(uy, cadd(next.c0, cmul_i(next.c1)));        // U_y(s) c(s+y)
+            const C Dd = cmulc(uy_prev, csub(prev.c0, cmul_i(prev.c1)));  // conj(U_y(s-y)) d(s-y)
+
+            Spinor<T> o;
+            C h0 = cadd(cadd(A, B), cadd(Cc, Dd));
+            C h1 = cadd(csub(B, A), cmul_i(csub(Dd, Cc)));
+            o.c0.x = fma(diag, cur.c0.x, half * h0.x); o.c0.y = fma(diag, cur.c0.y, half * h0.y);
+            o.c1.x = fma(diag, cur.c1.x, half * h1.x); o.c1.y = fma(diag, cur.c1.y, half * h1.y);
+            if (MODE == 1) {
+                Spinor<T> bb = load_spinor<T>(b, s);
+                if (DOTS && active) red[3] += (double)bb.c0.x * bb.c0.x + (double)bb.c0.y * bb.c0.y
+                                            + (double)bb.c1.x * bb.c1.x + (double)bb.c1.y * bb.c1.y;
+                o.c0 = csub(bb.c0, o.c0); o.c1 = csub(bb.c1, o.c1);
+            }
+            if (active) {
+                store_spinor<T>(out, s, o);
+                if (DOTS) {
+                    red[0] += (double)o.c0.x * o.c0.x + (double)o.c0.y * o.c0.y
+                            + (double)o.c1.x * o.c1.x + (double)o.c1.y * o.c1.y;
+                    // <out, in> = conj(out) * in
+                    red[1] += (double)o.c0.x * cur.c0.x + (double)o.c0.y * cur.c0.y
+                            + (double)o.c1.x * cur.c1.x + (double)o.c1.y * cur.c1.y;
+                    red[2] += (double)o.c0.x * cur.c0.y - (double)o.c0.y * cur.c0.x
+                            + (double)o.c1.x * cur.c1.y - (double)o.c1.y * cur.c1.x;
+                }
+            }
+            prev = cur; cur = next; uy_prev = uy;
+        }
+    }
+    if (DOTS) grid_reduce<4, WX>(red, partials, counter, dots, blockIdx.x, gridDim.x);
+}
+
+// materialise D[s][5][n][n] (column-major blocks) for the level-0 operator
+template <typename T>
+__global__ void lvl0_matrix_kernel(cplx<T>* __restrict__ D, const cplx<T>* __restrict__ U,
+                                   const cplx<T>* __restrict__ U_lo, T diag, int wilson, int Lx, int Ly) {
+    using C = cplx<T>;
+    const size_t S = (size_t)Lx * Ly;
+    for (size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x; s < S; s += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(s / Lx), x = (int)(s - (size_t)y * Lx);
+        const int xm = (x == 0) ? Lx - 1 : x - 1;
+        const C ux = U[2 * s], uy = U[2 * s + 1];
+        const C uxm = cconj(U[2 * ((size_t)y * Lx + xm)]);
+        const C uym = cconj(y == 0 ? U_lo[2 * (size_t)x + 1] : U[2 * ((size_t)(y - 1) * Lx + x) + 1]);
+        const C zero = mk<T>(0, 0);
+        if (!wilson) {   // gauged Laplace, S6/level.h:139-153: D0 = -(4+m) (diag carries the sign)
+            C* d = D + s * 5;
+            d[0] = mk<T>(diag, 0); d[1] = ux; d[2] = uxm; d[3] = uy; d[4] = uym;
+        } else {         // S6/level.h:155-172; block (i,j) stored at j*2+i
+            C* d = D + s * 20;
+            const T h = (T)0.5;
+            d[0] = mk<T>(diag, 0); d[1] = zero; d[2] = zero; d[3] = mk<T>(diag, 0);
+            // 1/2 (1 - s1) = 1/2 [[1,-1],[-1,1]]
+            C p = cscale(ux, h), mneg = cscale(ux, -h);
+            d[4] = p; d[5] = mneg; d[6] = mneg; d[7] = p;
+            // 1/2 (1 + s1) = 1/2 [[1,1],[1,1]]
+            p = cscale(uxm, h);
+            d[8] = p; d[9] = p; d[10] = p; d[11] = p;
+            // 1/2 (1 - s2) = 1/2 [[1, i],[-i, 1]]  -> (0,0)=1,(1,0)=-i,(0,1)=i,(1,1)=1 (column-major order)
+            p = cscale(uy, h);
+            d[12] = p; d[13] = cmul_mi(p); d[14] = cmul_i(p); d[15] = p;
+            // 1/2 (1 + s2) = 1/2 [[1,-i],[i,1]]
+            p = cscale(uym, h);
+            d[16] = p; d[17] = cmul_i(p); d[18] = cmul_mi(p); d[19] = p;
+        }
+    }
+}
+
+template <typename T>
+int launch_wilson(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, const void* in_hi, const void* U,
+                  const void* U_lo, const void* b, double mass, int Lx, int Ly, int mode, double* dots,
+                  cudaStream_t st) {
+    using C = cplx<T>;
+    const int nwork = ((Lx + WX - 1) / WX) * ((Ly + RY - 1) / RY);
+    int grid = nwork < MG2D_MAX_PARTIALS ? nwork : MG2D_MAX_PARTIALS;
+    const int cap = ctx->num_sms * 16;
+    if (grid > cap) grid = cap;
+    const T diag = (T)(2.0 + mass);
+#define WL(MODE, DOTS)                                                                                      \
+    wilson_march_kernel<T, MODE, DOTS><<<grid, WX, 0, st>>>((C*)out, (const C*)in, (const C*)in_lo,          \
+        (const C*)in_hi, (const C*)U, (const C*)U_lo, (const C*)b, diag, Lx, Ly, ctx->partials, ctx->counter, dots)
+    if (mode == MG2D_MODE_APPLY) { if (dots) WL(0, true); else WL(0, false); }
+    else                         { if (dots) WL(1, true); else WL(1, false); }
+#undef WL
+    return mg2d_check_launch(ctx, "mg2d_wilson_apply");
+}
+
+}  // namespace
+
+extern "C" int mg2d_wilson_apply(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, const void* in_hi,
+                                 const void* U, const void* U_lo, const void* b, double mass, int Lx, int Ly,
+                                 int mode, int dtype, double* dots, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!out || !in || !in_lo || !in_hi || !U || !U_lo || Lx < 2 || Ly < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_apply: bad argument");
+    if (mode == MG2D_MODE_RESID && !b) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_apply: MODE_RESID needs b");
+    if (mode != MG2D_MODE_APPLY && mode != MG2D_MODE_RESID) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_apply: bad mode");
+    if (out == in) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_apply: out must not alias in");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return launch_wilson<double>(ctx, out, in, in_lo, in_hi, U, U_lo, b, mass, Lx, Ly, mode, dots, st);
+    if (dtype == MG2D_C64)  return launch_wilson<float>(ctx, out, in, in_lo, in_hi, U, U_lo, b, mass, Lx, Ly, mode, dots, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_apply: bad dtype");
+}
+
+extern "C" int mg2d_lvl0_matrix(mg2d_ctx* ctx, void* D, const void* U, const void* U_lo, double mass, int stencil,
+                                int Lx, int Ly, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!D || !U || !U_lo || Lx < 1 || Ly < 1 || (stencil != 0 && stencil != 1)) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_lvl0_matrix: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t S = (size_t)Lx * Ly;
+    int grid = (int)((S + 255) / 256); if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    const int wilson = stencil == 0;
+    const double diag = wilson ? (2.0 + mass) : -(4.0 + mass);
+    if (dtype == MG2D_C128) lvl0_matrix_kernel<double><<<grid, 256, 0, st>>>((double2*)D, (const double2*)U, (const double2*)U_lo, diag, wilson, Lx, Ly);
+    else if (dtype == MG2D_C64) lvl0_matrix_kernel<float><<<grid, 256, 0, st>>>((float2*)D, (const float2*)U, (const float2*)U_lo, (float)diag, wilson, Lx, Ly);
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_lvl0_matrix: bad dtype");
+    return mg2d_check_launch(ctx, "mg2d_lvl0_matrix");
+}

@@ -1,0 +1,520 @@
+"""Host-side mirror of the reference's solver objects, driving the sm_100a kernels of libmg2d_sm100.so.
+
+Reference -> here (S6 = code/6_ntl-mg_new_code/3_combining_laplace_and_wilson/):
+  class Level : Near_null  (S6/level.h, S6/near_null.h)      -> class Level   (same method names, f_ prefix dropped)
+  free functions of S6/modules_main.h                       -> module functions of the same names
+  main()                   (S6/mgrid_ntl.cpp:29-73)         -> setup() / solve() / run_reference_flow()
+
+Every numerical operation is a CUDA kernel behind the C ABI (include/mg2d.h); torch supplies device memory,
+streams and (multi-GPU) torch.distributed.  There is no CPU path: constructing an MG without the library or
+without an sm_100 device raises.
+
+Layouts (device): fields [S, n]; links U [S, 2]; projector phi_null [S, nc, nf] (reference layout);
+operator D [S, 5, n, n] with COLUMN-major n x n blocks, i.e. D[s, k, j, i] = D_ref(s, k)(i, j).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Context, MG2DError
+from .params import MGParams
+from .rng import StdMT19937
+
+_DT = {"complex128": (torch.complex128, _lib.C128), "complex64": (torch.complex64, _lib.C64)}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def D_to_reference_layout(D: torch.Tensor) -> torch.Tensor:
+    """[S,5,j,i] (device layout) <-> [S,5,i,j] (D(s,k)(i,j) of the reference).  Involution."""
+    return D.transpose(-1, -2).contiguous()
+
+
+class Level:
+    """class Level : public Near_null (S6/level.h:3-39, S6/near_null.h:9-22): phi, r, D, phi_null of one
+    multigrid level, plus the kernel workspace (MR residual / direction, D0^-1, reduction slots)."""
+
+    def __init__(self, mg: "MG", lvl: int):
+        self.mg, self.lvl = mg, lvl
+        p = mg.p
+        self.L = p.size[lvl]
+        self.n = p.n_dof[lvl]
+        self.S = self.L * self.L
+        self.nc = p.n_dof[lvl + 1] if lvl < p.nlevels else None
+        self.phi = None
+        self.r = None
+        self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
+        self.D0inv = None
+        self.phi_null = None   # [S,nc,nf]
+        self.U = None          # level 0 only: links [S,2]
+        self.matrix_free = False
+        self._work = {}
+
+    # ---- plumbing -------------------------------------------------------------------------------------
+    def new_field(self, nvec: int | None = None, zero: bool = True):
+        shape = (self.S, self.n) if nvec is None else (nvec, self.S, self.n)
+        f = torch.zeros if zero else torch.empty
+        return f(shape, dtype=self.mg.tdtype, device=self.mg.device)
+
+    def work(self, name: str, nvec: int | None = None):
+        key = (name, nvec)
+        if key not in self._work:
+            self._work[key] = self.new_field(nvec)
+        return self._work[key]
+
+    def dots(self, name: str = "dots"):
+        if name not in self._work:
+            self._work[name] = torch.zeros(64 * 4, dtype=torch.float64, device=self.mg.device)
+        return self._work[name]
+
+    def _halo(self, t: torch.Tensor):
+        """(lo, hi) row pointers for a field of this level: periodic wrap rows on one GPU."""
+        es = t.element_size() * self.n
+        base = t.data_ptr()
+        return base + (self.L - 1) * self.L * es, base
+
+    def init_level(self, gen: StdMT19937 | None):
+        """f_init_level (S6/level.h:42-53): phi, r, phi_null drawn in this order (gen None -> ones, rand=0)."""
+        mg, p = self.mg, self.mg.p
+        draw = (lambda k: gen.uniform_pm_pi(k)) if gen is not None else (lambda k: np.ones(k))
+        self.phi = mg.to_device(draw(self.S * self.n).reshape(self.S, self.n))
+        self.r = mg.to_device(draw(self.S * self.n).reshape(self.S, self.n))
+        if self.lvl != p.nlevels:
+            self.phi_null = mg.to_device(draw(self.S * self.nc * self.n).reshape(self.S, self.nc, self.n))
+
+    def define_source(self):
+        """f_define_source (S6/level.h:55-59)."""
+        self.r[2 + 2 * self.mg.p.L, 0] = 5.0
+
+    # ---- operators ------------------------------------------------------------------------------------
+    def compute_lvl0_matrix(self, U: torch.Tensor, store: bool = True):
+        """f_compute_lvl0_matrix (S6/level.h:131-175).  With store=False only the links are kept and the
+        Wilson operator is applied matrix-free."""
+        mg, p = self.mg, self.mg.p
+        assert self.lvl == 0
+        self.U = U
+        if store:
+            self.D = torch.empty((self.S, 5, self.n, self.n), dtype=mg.tdtype, device=mg.device)
+            u_lo = U.data_ptr() + (self.L - 1) * self.L * 2 * U.element_size()
+            mg.ctx.call("mg2d_lvl0_matrix", _ptr(self.D), _ptr(U), u_lo, float(p.mass),
+                        0 if p.stencil == "wilson" else 1, self.L, self.L, mg.dcode, _stream())
+            self.D0inv = None
+        self.matrix_free = not store
+
+    def _stencil(self, out, vin, b, mode, dots, nvec=1):
+        mg = self.mg
+        if out.data_ptr() == vin.data_ptr():
+            raise ValueError("stencil output must not alias its input")
+        lo, hi = self._halo(vin if nvec == 1 else vin[0])
+        if self.matrix_free:
+            if nvec != 1:
+                for v in range(nvec):
+                    self._stencil(out[v], vin[v], None if b is None else b[v], mode,
+                                  None if dots is None else dots[4 * v:], 1)
+                return
+            u_lo = self.U.data_ptr() + (self.L - 1) * self.L * 2 * self.U.element_size()
+            mg.ctx.call("mg2d_wilson_apply", _ptr(out), _ptr(vin), lo, hi, _ptr(self.U), u_lo, _ptr(b),
+                        float(mg.p.mass), self.L, self.L, mode, mg.dcode, _ptr(dots), _stream())
+        else:
+            vs = self.S * self.n
+            mg.ctx.call("mg2d_stencil_apply", _ptr(out), _ptr(vin), lo, hi, _ptr(self.D), _ptr(b), self.n,
+                        self.L, self.L, mode, mg.dcode, nvec, vs, vs, _ptr(dots), _stream())
+
+    def apply_D(self, v_out, v_in):
+        """f_apply_D (S6/level.h:251-265): v_out = D v_in."""
+        self._stencil(v_out, v_in, None, _lib.MODE_APPLY, None)
+
+    def residue(self, rtemp):
+        """f_residue (S6/level.h:61-77): rtemp = r - D phi."""
+        self._stencil(rtemp, self.phi, self.r, _lib.MODE_RESID, None)
+
+    def residue_mag_async(self, out2: torch.Tensor | None = None):
+        """Launch the fused residual + norms of f_get_residue_mag; returns the device dots tensor
+        ([0] = |r - D phi|^2, [3] = |r|^2).  No host sync."""
+        d = self.dots("resmag")
+        self._stencil(self.work("rtemp"), self.phi, self.r, _lib.MODE_RESID, d)
+        self.mg.allreduce(d[:4])
+        return d
+
+    def get_residue_mag(self) -> float:
+        """f_get_residue_mag (S6/level.h:79-98): |r - D phi| / |r|."""
+        d = self.residue_mag_async().cpu()
+        return math.sqrt(d[0].item()) / math.sqrt(d[3].item())
+
+    def _ensure_D0inv(self):
+        if self.D0inv is None:
+            if self.D is None:
+                raise MG2DError("Gauss-Seidel / Jacobi need the stored operator (matrix_free=False)")
+            self.D0inv = torch.empty((self.S, self.n, self.n), dtype=self.mg.tdtype, device=self.mg.device)
+            self.mg.ctx.call("mg2d_block_inverse", _ptr(self.D0inv), _ptr(self.D), self.n, self.S, self.mg.dcode, _stream())
+
+    def relax(self, num_iter: int, gs_flag: int | None = None, phi=None, r="self", smoother: str | None = None):
+        """f_relax (S6/level.h:100-128).  gs_flag 1 = lexicographic Gauss-Seidel, 0 = Jacobi (reference);
+        smoother='mr' = minimal residual (north_star).  phi may be a batch [nvec, S, n]; r=None means r=0."""
+        mg = self.mg
+        if smoother is None:
+            smoother = mg.p.smoother if gs_flag is None else ("gs" if gs_flag == 1 else "jacobi")
+        phi = self.phi if phi is None else phi
+        r = self.r if isinstance(r, str) else r
+        nvec = 1 if phi.dim() == 2 else phi.shape[0]
+        vs = self.S * self.n
+        if num_iter <= 0:
+            return
+        if smoother == "gs":
+            self._ensure_D0inv()
+            mg.ctx.call("mg2d_relax_gs", _ptr(phi), _ptr(self.D), _ptr(self.D0inv), _ptr(r), self.n, self.L,
+                        num_iter, mg.dcode, nvec, vs, _stream())
+        elif smoother == "jacobi":
+            self._ensure_D0inv()
+            tmp = self.work("jacobi_tmp", None if nvec == 1 else nvec)
+            cur, nxt = phi, tmp
+            for _ in range(num_iter):
+                lo, hi = self._halo(cur if nvec == 1 else cur[0])
+                mg.ctx.call("mg2d_relax_jacobi", _ptr(nxt), _ptr(cur), lo, hi, _ptr(self.D), _ptr(self.D0inv),
+                            _ptr(r), self.n, self.L, self.L, mg.dcode, nvec, vs, vs, _stream())
+                cur, nxt = nxt, cur
+            if cur.data_ptr() != phi.data_ptr():
+                mg.ctx.call("mg2d_copy", _ptr(phi), _ptr(cur), phi.numel(), mg.dcode, _stream())
+        elif smoother == "mr":
+            key = None if nvec == 1 else nvec
+            res, t, d = self.work("mr_res", key), self.work("mr_t", key), self.dots("mr")
+            b = r if r is not None else self.work("zero_rhs", key)
+            self._stencil(res, phi, b, _lib.MODE_RESID, None, nvec)
+            for _ in range(num_iter):
+                self._stencil(t, res, None, _lib.MODE_APPLY, d, nvec)
+                mg.allreduce(d[:4 * nvec])
+                mg.ctx.call("mg2d_mr_update", _ptr(phi), _ptr(res), _ptr(t), _ptr(d), float(mg.p.mr_omega),
+                            vs, mg.dcode, nvec, vs, _stream())
+        else:
+            raise ValueError(smoother)
+
+    # ---- near-null vectors (class Near_null) -------------------------------------------------------------
+    def near_null(self):
+        """f_near_null (S6/level.h:177-249): null_iters relaxation sweeps on D v = 0 in chunks of null_chunk
+        with a global renormalisation (f_g_norm, S6/modules_indiv.h:70-92) after each chunk, all vectors
+        batched; then conjugate (+ chirality split for wilson) into the rows of phi_null."""
+        mg, p = self.mg, self.mg.p
+        nf, nc = self.n, self.nc
+        wilson = p.stencil == "wilson"
+        nvec = nc // 2 if wilson else nc
+        num = max(p.null_iters // p.null_chunk, 1)
+        V = self.phi_null[:, :nvec, :].permute(1, 0, 2).contiguous()     # rows d1 of the random start
+        vs = self.S * nf
+        nrm = self.dots("nullnorm")
+        for _ in range(num):
+            self.relax(p.null_chunk, phi=V, r=None)
+            for v in range(nvec):
+                mg.ctx.call("mg2d_norm2", _ptr(V[v]), vs, mg.dcode, _ptr(nrm[v:]), _stream())
+            mg.allreduce(nrm[:nvec])
+            for v in range(nvec):
+                mg.ctx.call("mg2d_scale_inv_norm", _ptr(V[v]), _ptr(nrm[v:]), vs, mg.dcode, _stream())
+        mg.ctx.call("mg2d_pack_null", _ptr(self.phi_null), _ptr(V), nvec, vs, nf, nc, self.S, int(wilson),
+                    mg.dcode, _stream())
+
+    def norm_nn(self, quad: int):
+        """f_norm_nn (S6/near_null.h:24-48)."""
+        mg = self.mg
+        mg.ctx.call("mg2d_norm_nn", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad, mg.dcode, _stream())
+
+    def ortho(self, quad: int):
+        """f_ortho (S6/near_null.h:97-173)."""
+        mg = self.mg
+        mg.ctx.call("mg2d_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad, mg.dcode,
+                    _ptr(mg.status), _stream())
+
+    def check_ortho(self, quad: int) -> float:
+        """f_check_ortho (S6/near_null.h:175-214): worst |<null_d1, null_d2>| over aggregates."""
+        mg = self.mg
+        out = self.dots("ortho_check")
+        mg.ctx.call("mg2d_check_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad,
+                    mg.dcode, _ptr(out), _stream())
+        return float(out[0].item())
+
+    def restriction(self, vec_c, vec_f, quad: int):
+        """f_restriction (S6/near_null.h:217-240): vec_c = P vec_f."""
+        mg = self.mg
+        mg.ctx.call("mg2d_restrict", _ptr(vec_c), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.L,
+                    mg.p.block, quad, mg.dcode, _stream())
+
+    def prolongation(self, vec_f, vec_c, quad: int, zero_vc: bool = False):
+        """f_prolongation (S6/near_null.h:242-264): vec_f += P^dagger vec_c.  `self` is the FINE level."""
+        mg = self.mg
+        mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(vec_c), _ptr(self.phi_null), self.n, self.nc, self.L, self.L,
+                    mg.p.block, quad, int(zero_vc), mg.dcode, _stream())
+
+
+# ==========================================================================================================
+class MG:
+    """The LVL[] / NTL[][4] arrays of main() (S6/mgrid_ntl.cpp:38-45) on one GPU."""
+
+    def __init__(self, params: MGParams, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise MG2DError("2d_multigrid_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.p = params
+        self.device_index = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", self.device_index)
+        self.ctx = Context(self.device_index)
+        self.tdtype, self.dcode = _DT[params.dtype]
+        self.status = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.LVL = [Level(self, l) for l in range(params.nlevels + 1)]
+        self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
+        self.info = {}
+
+    def to_device(self, a) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(a)).to(self.tdtype).to(self.device)
+
+    def allreduce(self, t):   # single GPU: nothing to do (multi-GPU strips override this)
+        return
+
+    # ---- main() steps ------------------------------------------------------------------------------------
+    def init_reference_fields(self):
+        """The draws of main() (S6/mgrid_ntl.cpp:38-48) in the reference's order."""
+        gen = StdMT19937(self.p.seed)
+        for lv in self.LVL:
+            lv.init_level(gen)
+        init_NTL(self, gen)
+        self.LVL[0].define_source()
+
+    def init_fields(self, generator_seed: int | None = None):
+        """Device-side initialisation for lattices too large for the host RNG stream: phi = 0, r = 0,
+        phi_null ~ U(-pi, pi) from torch's generator."""
+        g = torch.Generator(device=self.device)
+        g.manual_seed(self.p.seed if generator_seed is None else generator_seed)
+        for lv in self.LVL:
+            lv.phi, lv.r = lv.new_field(), lv.new_field()
+            if lv.lvl != self.p.nlevels:
+                re = (torch.rand((lv.S, lv.nc, lv.n), generator=g, dtype=torch.float64, device=self.device) * 2 - 1) * math.pi
+                lv.phi_null = re.to(self.tdtype)
+
+    def set_gauge(self, U):
+        U = torch.as_tensor(U).to(self.tdtype).to(self.device).contiguous()
+        self.LVL[0].compute_lvl0_matrix(U, store=True)
+
+
+# ---- modules_main.h --------------------------------------------------------------------------------------
+def init_NTL(mg: MG, gen: StdMT19937 | None):
+    """f_init_NTL (S6/modules_main.h:7-37)."""
+    p = mg.p
+    if not (p.ntl and p.nlevels > 0):
+        return
+    draw = (lambda k: gen.uniform_pm_pi(k)) if gen is not None else (lambda k: np.ones(k))
+    lo = p.nlevels - 1
+    for q in range(p.n_copies):
+        lv = mg.NTL[lo][q]
+        lv.phi = mg.to_device(draw(lv.S * lv.n).reshape(lv.S, lv.n))
+        lv.r = mg.to_device(draw(lv.S * lv.n).reshape(lv.S, lv.n))
+        lv.phi_null = mg.to_device(draw(lv.S * lv.nc * lv.n).reshape(lv.S, lv.nc, lv.n))
+    for q in range(p.n_copies):
+        lv = mg.NTL[p.nlevels][q]
+        lv.phi = mg.to_device(draw(lv.S * lv.n).reshape(lv.S, lv.n))
+        lv.r = mg.to_device(draw(lv.S * lv.n).reshape(lv.S, lv.n))
+
+
+def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
+    """f_compute_coarse_matrix (S6/modules_main.h:81-185): lvl_c.D = P D_f P^dagger with P = lvl_P.phi_null."""
+    mg = lvl_f.mg
+    nf, nc = lvl_f.n, lvl_P.nc
+    if lvl_f.D is None:
+        raise MG2DError("compute_coarse_matrix needs the stored fine operator")
+    lvl_c.D = torch.empty((lvl_c.S, 5, nc, nc), dtype=mg.tdtype, device=mg.device)
+    lvl_c.D0inv = None
+    P = lvl_P.phi_null
+    es = P.element_size() * nc * nf
+    p_lo, p_hi = P.data_ptr() + (lvl_f.L - 1) * lvl_f.L * es, P.data_ptr()
+    mg.ctx.call("mg2d_coarse_matrix", _ptr(lvl_c.D), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.L,
+                mg.p.block, quad, mg.dcode, _stream())
+
+
+def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
+    """f_compute_near_null (S6/modules_main.h:187-222).  gen_null=0: phi_null rows are already supplied."""
+    p = mg.p
+    quad = p.quad if quad is None else quad
+    worst = []
+    for lvl in range(p.nlevels):
+        lv = mg.LVL[lvl]
+        if gen_null == 1:
+            lv.near_null()
+        lv.norm_nn(quad)
+        lv.ortho(quad)
+        lv.ortho(quad)
+        worst.append(lv.check_ortho(quad))
+        compute_coarse_matrix(mg.LVL[lvl + 1], lv, lv, quad)
+    if p.ntl:
+        lo = p.nlevels - 1
+        for q in range(p.n_copies):
+            nt = mg.NTL[lo][q]
+            nt.phi_null = mg.LVL[lo].phi_null.clone()
+            nt.norm_nn(quad)
+            nt.ortho(q + 1)
+            nt.ortho(q + 1)
+            worst.append(nt.check_ortho(q + 1))
+            compute_coarse_matrix(mg.NTL[p.nlevels][q], mg.LVL[lo], nt, q + 1)
+    st = mg.status.cpu()
+    if int(st[0]) != 0:
+        raise FloatingPointError(f"near-null orthonormalisation failed (status {int(st[0])}): NaN or tiny norm "
+                                 "(S6/modules_indiv.h:119-126, S6/near_null.h:149-159)")
+    mg.info["ortho_worst"] = worst
+    if p.matrix_free:   # the stored level-0 operator was only needed for the Galerkin product
+        mg.LVL[0].D = None
+        mg.LVL[0].D0inv = None
+        mg.LVL[0].matrix_free = True
+
+
+def restriction_res(res_c, L_residue: Level, L_restrict: Level, quad: int):
+    """f_restriction_res (S6/modules_main.h:224-241): res_c = P (r - D phi)."""
+    rtemp = L_residue.work("rtemp")
+    L_residue.residue(rtemp)
+    L_restrict.restriction(res_c, rtemp, quad)
+
+
+def prolongate_phi(phi_f, phi_c, LVLP: Level, quad: int):
+    """f_prolongate_phi (S6/modules_main.h:243-252): phi_f += P^dagger phi_c ; phi_c = 0."""
+    LVLP.prolongation(phi_f, phi_c, quad, zero_vc=True)
+
+
+def MG_simple(mg: MG):
+    """f_MG_simple (S6/modules_main.h:255-280)."""
+    p, LVL = mg.p, mg.LVL
+    if p.nlevels > 0:
+        for lvl in range(p.nlevels):
+            LVL[lvl].relax(p.n_smooth)
+            restriction_res(LVL[lvl + 1].r, LVL[lvl], LVL[lvl], p.quad)
+        for lvl in range(p.nlevels, -1, -1):
+            LVL[lvl].relax(p.n_smooth)
+            if lvl > 0:
+                prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad)
+    else:
+        LVL[0].relax(p.n_smooth)
+
+
+def min_res(mg: MG, num_copies: int, level: int) -> torch.Tensor:
+    """f_min_res (S6/modules_main.h:283-373): weights a_q (device tensor, 2*num_copies doubles)."""
+    p = mg.p
+    lv = mg.LVL[level]
+    E = mg._ntl_fields(level)           # [4, S, n] contiguous views of NTL[level][q].phi
+    T = lv.work("minres_t", 4)
+    for q in range(num_copies):
+        lv.apply_D(T[q], E[q])
+    vs = lv.S * lv.n
+    buf = lv.dots("minres")
+    gram, src, a = buf[0:32], buf[32:40], buf[40:48]
+    mg.ctx.call("mg2d_cdot_batch", _ptr(E), vs, num_copies, _ptr(T), vs, num_copies, vs, mg.dcode, _ptr(gram), _stream())
+    if p.stencil == "laplace":   # src_i = <e_i, r>   (:336-340)
+        mg.ctx.call("mg2d_cdot_batch", _ptr(E), vs, num_copies, _ptr(lv.r), vs, 1, vs, mg.dcode, _ptr(src), _stream())
+    else:                        # src_i = <r, D e_i> (:358-366)
+        mg.ctx.call("mg2d_cdot_batch", _ptr(lv.r), vs, 1, _ptr(T), vs, num_copies, vs, mg.dcode, _ptr(src), _stream())
+    mg.allreduce(buf[0:40])
+    mg.ctx.call("mg2d_minres_solve", _ptr(gram), _ptr(src), num_copies, _ptr(a), _stream())
+    return a
+
+
+def scale_phi(mg: MG, L1: Level, a, num_copies: int, lvl: int):
+    """f_scale_phi (S6/modules_main.h:375-384)."""
+    E = mg._ntl_fields(lvl)
+    vs = L1.S * L1.n
+    mg.ctx.call("mg2d_scale_phi", _ptr(L1.phi), _ptr(E), vs, _ptr(a), num_copies, vs, mg.dcode, _stream())
+
+
+def _ntl_fields(self: MG, level: int):
+    """The phi of NTL[level][0..3] live in one [4,S,n] buffer so that the Gram matrix is one batched launch."""
+    key = ("ntl_phi", level)
+    if key not in self.info:
+        lv = self.LVL[level]
+        buf = lv.new_field(4)
+        for q in range(4):
+            old = self.NTL[level][q].phi
+            if old is not None:
+                buf[q].copy_(old)
+            self.NTL[level][q].phi = buf[q]
+        self.info[key] = buf
+    return self.info[key]
+
+
+MG._ntl_fields = _ntl_fields
+
+
+def MG_ntl(mg: MG):
+    """f_MG_ntl (S6/modules_main.h:386-439).  Returns the device tensor of the 4 complex copy weights."""
+    p, LVL, NTL = mg.p, mg.LVL, mg.NTL
+    a = None
+    for lvl in range(p.nlevels):
+        LVL[lvl].relax(p.n_smooth)
+        if lvl != p.nlevels - 1:
+            restriction_res(LVL[lvl + 1].r, LVL[lvl], LVL[lvl], p.quad)
+        else:
+            rtemp = LVL[lvl].work("rtemp")
+            LVL[lvl].residue(rtemp)
+            for q in range(p.n_copies):
+                NTL[lvl][q].restriction(NTL[lvl + 1][q].r, rtemp, q + 1)
+    for lvl in range(p.nlevels, -1, -1):
+        if lvl == p.nlevels:
+            mg._ntl_fields(lvl - 1)
+            for q in range(p.n_copies):
+                NTL[lvl][q].relax(p.n_smooth)
+                prolongate_phi(NTL[lvl - 1][q].phi, NTL[lvl][q].phi, NTL[lvl - 1][q], q + 1)
+            if p.min_res_flag == 1:
+                a = min_res(mg, p.n_copies, lvl - 1)
+            else:
+                a = LVL[lvl - 1].dots("minres")[40:48]
+                a.zero_()
+                a[0:2 * p.n_copies:2] = 1.0 / p.n_copies
+            scale_phi(mg, LVL[lvl - 1], a, p.n_copies, lvl - 1)
+        else:
+            LVL[lvl].relax(p.n_smooth)
+            if lvl > 0:
+                prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad)
+    return a
+
+
+def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, check_every: int = 1,
+               record_phi: bool = False):
+    """f_perform_MG (S6/modules_main.h:442-481): cycles until |r - D phi|/|r| < tol; diverged if > 1e6.
+    The residual norms are produced on the device by the fused residual kernel; the host reads them every
+    `check_every` cycles (1 = the reference's behaviour)."""
+    p = mg.p
+    tol = p.tol if tol is None else tol
+    max_iters = p.max_iters if max_iters is None else max_iters
+    info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False, "phi_hist": []}
+    hist = torch.zeros((max(check_every, 1), 4), dtype=torch.float64, device=mg.device)
+    whist = torch.zeros((max(check_every, 1), 8), dtype=torch.float64, device=mg.device)
+    ntl = p.ntl and p.nlevels > 0
+    it = 0
+    while it < max_iters:
+        nb = min(check_every, max_iters - it)
+        for k in range(nb):
+            if record_phi:
+                info["phi_hist"].append(mg.LVL[0].phi.clone())
+            if ntl:
+                a = MG_ntl(mg)
+                whist[k].copy_(a[:8])
+            else:
+                MG_simple(mg)
+            d = mg.LVL[0].residue_mag_async()
+            hist[k].copy_(d[:4])
+        h = hist[:nb].cpu()
+        wh = whist[:nb].cpu() if ntl else None
+        for k in range(nb):
+            resmag = math.sqrt(h[k, 0].item()) / math.sqrt(h[k, 3].item()) if h[k, 3].item() > 0 else float("nan")
+            info["resnorms"].append(resmag)
+            if ntl:
+                w = wh[k].numpy()
+                info["ntl_weights"].append(w[0::2] + 1j * w[1::2])
+            info["iters"] = it + k + 1
+            if resmag < tol:
+                info["converged"] = True
+                return info
+            if resmag > 1e6 or math.isnan(resmag):
+                info["diverged"] = True
+                return info
+        it += nb
+    return info

@@ -1,0 +1,164 @@
+/* mg2d.h -- C ABI of libmg2d_sm100.so: the B200 (sm_100a) hot path of vmos1/2d_multigrid.
+ *
+ * The reference has no FFI: it is one C++ translation unit (S6/mgrid_ntl.cpp) whose hot path is the member
+ * functions of `class Level : Near_null` plus the free functions of modules_main.h.  Each entry point below
+ * replaces one of those functions (cited as S6/<file>:<lines>, S6 = code/6_ntl-mg_new_code/
+ * 3_combining_laplace_and_wilson/, S2 = code/2_scalar_2d_nontelescoping/telescoping_2d_laplace_Mgrid.cpp).
+ *
+ * Contract
+ *   - plain C: opaque handle, device pointers, ints, doubles, a cudaStream_t passed as void*.
+ *   - every call returns 0 on success or a negative MG2D_E* code; mg2d_last_error() gives the text.
+ *     No exceptions, no exit().
+ *   - the caller owns every field/operator buffer; the library owns only the reduction workspace created by
+ *     mg2d_create().  All calls are asynchronous on the given stream and never synchronise.
+ *   - one handle per GPU and per stream of work; a handle is not thread-safe.
+ *
+ * Data layout (device memory, x fastest: site s = x + y*Lx, as S6/level.h:69-75)
+ *   dtype MG2D_C128: interleaved (re,im) doubles;  MG2D_C64: interleaved floats.
+ *   field      v[s][n]                       n dof per site (level 0 Wilson: n = 2 spin components)
+ *   links      U[s][2]                       U_x(s), U_y(s)                     (S6/gauge.h:29-37)
+ *   operator   D[s][k][j][i]  k = 0..4       5-point block stencil, slot k: 0 self, 1 x+1, 2 x-1, 3 y+1, 4 y-1
+ *                                            (S6/level.h:8).  NOTE: each n x n block is stored COLUMN-major
+ *                                            (element (i,j) at j*n+i) so that a warp streams it coalesced.
+ *   projector  P[s][ic][jf]                  near-null vectors, nc x nf row-major per fine site
+ *                                            (phi_null(s)(ic,jf), S6/near_null.h:12)
+ *
+ * Strip decomposition (1-D in y): every stencil call works on `Ly` locally owned rows of width `Lx` and takes
+ * the two neighbouring rows as separate pointers `lo` (row y-1 of local row 0) and `hi` (row y+1 of the last
+ * local row).  On one GPU these are just the last / first owned row (periodic wrap).
+ */
+#ifndef MG2D_H
+#define MG2D_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mg2d_ctx mg2d_ctx;
+
+enum { MG2D_C128 = 0, MG2D_C64 = 1 };
+enum { MG2D_OK = 0, MG2D_EINVAL = -1, MG2D_ECUDA = -2, MG2D_EUNSUPPORTED = -3 };
+/* stencil modes */
+enum { MG2D_MODE_APPLY = 0,   /* out = D in                         Level::f_apply_D   S6/level.h:251-265 */
+       MG2D_MODE_RESID = 1 }; /* out = b - D in                     Level::f_residue   S6/level.h:61-77   */
+/* reduction slots written by the stencil calls when `dots` != NULL (doubles, device memory, per vector) */
+enum { MG2D_DOT_OUT2 = 0,     /* sum |out|^2                        f_get_residue_mag  S6/level.h:79-98   */
+       MG2D_DOT_OUTIN_RE = 1, /* Re <out, in> = Re sum conj(out) in (MR smoother)                          */
+       MG2D_DOT_OUTIN_IM = 2,
+       MG2D_DOT_B2 = 3,       /* sum |b|^2 (MODE_RESID only)                                               */
+       MG2D_NDOTS = 4 };
+
+int         mg2d_version(void);
+int         mg2d_create(mg2d_ctx** ctx, int device);
+int         mg2d_destroy(mg2d_ctx* ctx);
+const char* mg2d_last_error(mg2d_ctx* ctx);
+int         mg2d_launch_count(mg2d_ctx* ctx);          /* kernels launched through this handle so far */
+
+/* ---- level-0 operators, matrix free ------------------------------------------------------------------ */
+/* U(1) Wilson-Dirac: Level::f_compute_lvl0_matrix (wilson branch, S6/level.h:155-172) fused into
+ * Level::f_apply_D / f_residue / f_get_residue_mag.  n = 2.  `U_lo` = link row below local row 0. */
+int mg2d_wilson_apply(mg2d_ctx*, void* out, const void* in, const void* in_lo, const void* in_hi,
+                      const void* U, const void* U_lo, const void* b, double mass, int Lx, int Ly,
+                      int mode, int dtype, double* dots, void* stream);
+/* materialise the level-0 stencil D[s][5][n][n] (both branches of f_compute_lvl0_matrix, S6/level.h:131-175):
+ * stencil 0 = wilson (n=2), 1 = gauged laplace (n=1). */
+int mg2d_lvl0_matrix(mg2d_ctx*, void* D, const void* U, const void* U_lo, double mass, int stencil,
+                     int Lx, int Ly, int dtype, void* stream);
+
+/* ---- generic 5-point block stencil (all coarse levels; level 0 in reference-compat mode) -------------- */
+/* Level::f_apply_D / f_residue, n in {1,2,4,8,16,32}; nvec vectors `vstride` elements apart. */
+int mg2d_stencil_apply(mg2d_ctx*, void* out, const void* in, const void* in_lo, const void* in_hi,
+                       const void* D, const void* b, int n, int Lx, int Ly, int mode, int dtype,
+                       int nvec, long long vstride, long long hstride, double* dots, void* stream);
+/* D0inv[s] = inverse(D[s][0]) (column-major like D): the `D(x+y*L,0).inverse()` of S6/level.h:116, hoisted. */
+int mg2d_block_inverse(mg2d_ctx*, void* D0inv, const void* D, int n, long long nsites, int dtype, void* stream);
+/* Level::f_relax with gs_flag=0 (Jacobi), one sweep: out = -D0inv (sum_{k>=1} D_k in(s+d_k) - r). */
+int mg2d_relax_jacobi(mg2d_ctx*, void* out, const void* in, const void* in_lo, const void* in_hi,
+                      const void* D, const void* D0inv, const void* r, int n, int Lx, int Ly, int dtype,
+                      int nvec, long long vstride, long long hstride, void* stream);
+/* Level::f_relax with gs_flag=1: `num_iter` lexicographic Gauss-Seidel sweeps (x outer, y inner, S6/level.h:
+ * 113-123) executed as anti-diagonal wavefronts, which reproduces the sequential order exactly.  Whole
+ * periodic lattice on one GPU (Ly == Lx).  r == NULL means r = 0 (near-null relaxation, S6/level.h:196-198). */
+int mg2d_relax_gs(mg2d_ctx*, void* phi, const void* D, const void* D0inv, const void* r, int n, int L,
+                  int num_iter, int dtype, int nvec, long long vstride, void* stream);
+
+/* ---- BLAS-1 style fused updates ------------------------------------------------------------------------ */
+/* MR smoother update: alpha = omega * <t,res>/<t,t> read from `dots` (as written by a stencil call with
+ * in=res, out=t); phi += alpha res; res -= alpha t. */
+int mg2d_mr_update(mg2d_ctx*, void* phi, void* res, const void* t, const double* dots, double omega,
+                   long long nelem, int dtype, int nvec, long long vstride, void* stream);
+/* y += a x, a = (a_re, a_im), or a read from device `a_dev` (2 doubles) when a_dev != NULL. */
+int mg2d_axpy(mg2d_ctx*, void* y, const void* x, double a_re, double a_im, const double* a_dev,
+              long long nelem, int dtype, void* stream);
+int mg2d_zero(mg2d_ctx*, void* x, long long nelem, int dtype, void* stream);
+int mg2d_copy(mg2d_ctx*, void* dst, const void* src, long long nelem, int dtype, void* stream);
+/* dst = src converted between MG2D_C128 and MG2D_C64 */
+int mg2d_convert(mg2d_ctx*, void* dst, int dst_dtype, const void* src, int src_dtype, long long nelem, void* stream);
+/* out[0] = sum |x|^2 (f_g_norm, S6/modules_indiv.h:70-92) */
+int mg2d_norm2(mg2d_ctx*, const void* x, long long nelem, int dtype, double* out, void* stream);
+/* out[2*(i*ny+j) .. +1] = <x_i, y_j> = sum conj(x_i) y_j  (f_min_res Gram matrix, S6/modules_main.h:324-366) */
+int mg2d_cdot_batch(mg2d_ctx*, const void* x, long long xstride, int nx, const void* y, long long ystride,
+                    int ny, long long nelem, int dtype, double* out, void* stream);
+/* x *= 1/sqrt(norm2[0]) with norm2 on the device (rescale branch of f_g_norm, S6/modules_indiv.h:88-89) */
+int mg2d_scale_inv_norm(mg2d_ctx*, void* x, const double* norm2, long long nelem, int dtype, void* stream);
+
+/* ---- block aggregation: restriction / prolongation ------------------------------------------------------ */
+/* Near_null::f_restriction (S6/near_null.h:217-240): vc(X) = sum_{s in agg(X,quad)} P(s) vf(s).
+ * Lxf x Lyf fine sites (local strip), block x block aggregates, quad 1..4 (f_get_base_site,
+ * S6/modules_indiv.h:6-14; quad != 1 requires the whole periodic lattice on one GPU). */
+int mg2d_restrict(mg2d_ctx*, void* vc, const void* vf, const void* P, int nf, int nc, int Lxf, int Lyf,
+                  int block, int quad, int dtype, void* stream);
+/* Near_null::f_prolongation (S6/near_null.h:242-264): vf(s) += P(s)^dagger vc(X(s)); zero_vc != 0 also
+ * clears vc afterwards (f_prolongate_phi, S6/modules_main.h:243-252). */
+int mg2d_prolong_add(mg2d_ctx*, void* vf, void* vc, const void* P, int nf, int nc, int Lxf, int Lyf,
+                     int block, int quad, int zero_vc, int dtype, void* stream);
+
+/* ---- setup ---------------------------------------------------------------------------------------------- */
+/* Level::f_near_null tail (S6/level.h:217-246): P rows from the relaxed vectors V[v][s][nf]:
+ * laplace: P[s][v][:] = conj(V_v(s)); wilson: chirality split, row v gets the upper nf/2 components,
+ * row nc/2+v the lower ones, the rest 0. */
+int mg2d_pack_null(mg2d_ctx*, void* P, const void* V, int nvec, long long vstride, int nf, int nc,
+                   long long nsites, int wilson, int dtype, void* stream);
+/* Near_null::f_norm_nn (S6/near_null.h:24-48, f_block_norm S6/modules_indiv.h:94-135): every row of P
+ * normalised per aggregate. */
+int mg2d_norm_nn(mg2d_ctx*, void* P, int nf, int nc, int Lxf, int Lyf, int block, int quad, int dtype, void* stream);
+/* Near_null::f_ortho (S6/near_null.h:97-173): per-aggregate modified Gram-Schmidt, t -= (dot/|u|) u, then
+ * block-normalise.  `status` (device int, may be NULL) is set non-zero on NaN / tiny norms (:149-159). */
+int mg2d_ortho(mg2d_ctx*, void* P, int nf, int nc, int Lxf, int Lyf, int block, int quad, int dtype,
+               int* status, void* stream);
+/* Near_null::f_check_ortho (S6/near_null.h:175-214): out[0] = max over aggregates and d2<d1 of |<row d1,row d2>| */
+int mg2d_check_ortho(mg2d_ctx*, const void* P, int nf, int nc, int Lxf, int Lyf, int block, int quad, int dtype,
+                     double* out, void* stream);
+/* f_compute_coarse_matrix (S6/modules_main.h:81-185): Dc = P Df P^dagger split into the self block and the
+ * four face blocks.  P_lo / P_hi: projector rows below / above the local strip (quad 1 multi-GPU), else the
+ * periodic wrap rows. */
+int mg2d_coarse_matrix(mg2d_ctx*, void* Dc, const void* Df, const void* P, const void* P_lo, const void* P_hi,
+                       int nf, int nc, int Lxf, int Lyf, int block, int quad, int dtype, void* stream);
+
+/* ---- non-telescoping min-res (f_min_res, S6/modules_main.h:283-373) --------------------------------------- */
+/* Solve the ncopies x ncopies system A a = src with column-pivoted Householder QR (the
+ * `A.colPivHouseholderQr().solve(src)` of :371) on the device.  gram = output of mg2d_cdot_batch
+ * (A row-major, complex as 2 doubles), src likewise; a[2*q..] receives the weights. */
+int mg2d_minres_solve(mg2d_ctx*, const double* gram, const double* src, int ncopies, double* a, void* stream);
+/* f_scale_phi (S6/modules_main.h:375-384): phi += sum_q a_q e_q ; e_q = 0.  e_q are `estride` apart. */
+int mg2d_scale_phi(mg2d_ctx*, void* phi, void* e, long long estride, const double* a, int ncopies,
+                   long long nelem, int dtype, void* stream);
+
+/* ---- real scalar Laplace geometric MG, BASELINE config 1 (S2) -------------------------------------------- */
+/* relax (S2:46-72): num_iter lexicographic GS sweeps phi = scale (sum nbrs - b a^2), wavefront order. */
+int mg2d_s2_relax(mg2d_ctx*, double* phi, const double* b, int L, double scale, double a, int num_iter,
+                  int gs_flag, void* stream);
+/* f_projection (S2:74-110): res_c = 1/4 sum_{2x2, quadrant} (b - A phi). */
+int mg2d_s2_project(mg2d_ctx*, double* res_c, const double* b, const double* phi, int L, double scale, double a,
+                    int quad, void* stream);
+/* f_interpolate (S2:112-143): phi_f(4 sites) += phi_c ; phi_c = 0. */
+int mg2d_s2_interpolate(mg2d_ctx*, double* phi_f, double* phi_c, int Lc, int quad, void* stream);
+/* f_get_residue_mag (S2:23-44): out[0] = sum |b - A phi|. */
+int mg2d_s2_residue_mag(mg2d_ctx*, const double* phi, const double* b, int L, double scale, double a,
+                        double* out, void* stream);
+/* x *= s */
+int mg2d_s2_scale(mg2d_ctx*, double* x, double s, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MG2D_H */
