@@ -55,6 +55,23 @@ axpy_kernel(cplx<T>* __restrict__ y, const cplx<T>* __restrict__ x, double a_re,
     }
 }
 
+// y += sign * (num/den) * x  [and y2 += sign * (num/den) * x2], coefficients on the device (GCR updates)
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+axpy_ratio2_kernel(cplx<T>* __restrict__ y, const cplx<T>* __restrict__ x, cplx<T>* __restrict__ y2,
+                   const cplx<T>* __restrict__ x2, const double* __restrict__ num, const double* __restrict__ den,
+                   double sign, long long n) {
+    using C = cplx<T>;
+    const double d = den[0];
+    const C a = d > 0.0 ? mk<T>((T)(sign * num[0] / d), (T)(sign * num[1] / d)) : mk<T>(0, 0);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C yv = y[e];
+        cfma(yv, a, __ldg(x + e));
+        y[e] = yv;
+        if (y2) { C y2v = y2[e]; cfma(y2v, a, __ldg(x2 + e)); y2[e] = y2v; }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BL_THREADS) zero_kernel(cplx<T>* __restrict__ x, long long n) {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
@@ -343,4 +360,16 @@ extern "C" int mg2d_scale_phi(mg2d_ctx* ctx, void* phi, void* e, long long estri
         (scale_phi_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)phi, (double2*)e, estride, a, ncopies, nelem)),
         (scale_phi_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)phi, (float2*)e, estride, a, ncopies, nelem)),
         "mg2d_scale_phi");
+}
+
+extern "C" int mg2d_axpy_ratio2(mg2d_ctx* ctx, void* y, const void* x, void* y2, const void* x2, const double* num,
+                                const double* den, double sign, long long nelem, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!y || !x || !num || !den || nelem < 1 || ((y2 == nullptr) != (x2 == nullptr))) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_axpy_ratio2: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (axpy_ratio2_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)y, (const double2*)x, (double2*)y2, (const double2*)x2, num, den, sign, nelem)),
+        (axpy_ratio2_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)y, (const float2*)x, (float2*)y2, (const float2*)x2, num, den, sign, nelem)),
+        "mg2d_axpy_ratio2");
 }

@@ -129,6 +129,38 @@ stencil_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in, const 
                                          dots + 4 * v, blockIdx.x, gridDim.x);
 }
 
+// red-black Gauss-Seidel half sweep: sites with (x + y + yoff) % 2 == colour are updated in place from the
+// other colour (f_relax's update rule in the two-colour ordering).  Lx must be even.
+template <typename T, int N>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ D,
+                  const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, int Lx, int Ly, int colour, int yoff,
+                  long long vstride, long long hstride) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const int v = blockIdx.y;
+    phi += (size_t)v * vstride; lo += (size_t)v * hstride; hi += (size_t)v * hstride;
+    if (r) r += (size_t)v * vstride;
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    const long long nsteps = (S2 + GPB - 1) / GPB;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long h = step * GPB + grp;
+        const bool active = h < S2;
+        if (!active) h = S2 - 1;
+        const int y = (int)(h / Lh);
+        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        const size_t s = (size_t)y * Lx + x;
+        C acc = stencil_row<T, N, G, 1, true>(D + s * 5 * N * N, phi, lo, hi, x, y, Lx, Ly, g);
+        if (r) acc = csub(acc, __ldg(r + s * N + i));
+        C o = apply_minus_inv<T, N, G>(Dinv + s * N * N, acc, g);
+        if (active && jp == 0) phi[s * N + i] = o;
+    }
+}
+
 // lexicographic Gauss-Seidel by anti-diagonal wavefronts (cooperative launch, grid.sync between fronts)
 template <typename T, int N>
 __global__ void __launch_bounds__(ST_THREADS)
@@ -296,6 +328,32 @@ int dispatch_gs(mg2d_ctx* ctx, int n, void* phi, const void* D, const void* Dinv
 }
 
 template <typename T, int N>
+int launch_rb(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* D, const void* Dinv, const void* r,
+              int Lx, int Ly, int colour, int yoff, int nvec, long long vstride, long long hstride, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    const long long S2 = (long long)(Lx / 2) * Ly;
+    long long nsteps = (S2 + GPB - 1) / GPB;
+    long long cap = (long long)ctx->num_sms * 32;
+    dim3 grid((int)(nsteps < cap ? nsteps : cap), nvec);
+    stencil_rb_kernel<T, N><<<grid, ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, (const C*)D, (const C*)Dinv,
+                                                      (const C*)r, Lx, Ly, colour, yoff, vstride, hstride);
+    return mg2d_check_launch(ctx, "mg2d_relax_rb");
+}
+
+template <typename T>
+int dispatch_rb(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* hi, const void* D, const void* Dinv,
+                const void* r, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride, long long hstride,
+                cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_rb<T, N>(ctx, phi, lo, hi, D, Dinv, r, Lx, Ly, colour, yoff, nvec, vstride, hstride, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb: n_dof must be one of 1,2,4,8,16,32");
+    }
+}
+
+template <typename T, int N>
 int launch_inverse(mg2d_ctx* ctx, void* Dinv, const void* D, long long S, cudaStream_t st) {
     using C = cplx<T>;
     const size_t per_warp = 2 * (size_t)N * N * sizeof(C);
@@ -363,4 +421,16 @@ extern "C" int mg2d_block_inverse(mg2d_ctx* ctx, void* D0inv, const void* D, int
     if (dtype == MG2D_C128) return dispatch_inverse<double>(ctx, n, D0inv, D, nsites, st);
     if (dtype == MG2D_C64)  return dispatch_inverse<float>(ctx, n, D0inv, D, nsites, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_block_inverse: bad dtype");
+}
+
+extern "C" int mg2d_relax_rb(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* D,
+                             const void* D0inv, const void* r, int n, int Lx, int Ly, int colour, int yoff, int dtype,
+                             int nvec, long long vstride, long long hstride, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !D || !D0inv || Lx < 2 || (Lx & 1) || Ly < 1 || nvec < 1 || (colour != 0 && colour != 1))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb: bad argument (Lx must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_rb<double>(ctx, n, phi, phi_lo, phi_hi, D, D0inv, r, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
+    if (dtype == MG2D_C64)  return dispatch_rb<float>(ctx, n, phi, phi_lo, phi_hi, D, D0inv, r, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb: bad dtype");
 }

@@ -32,6 +32,18 @@ __device__ __forceinline__ Spinor<T> load_spinor(const cplx<T>* __restrict__ p, 
     }
     return r;
 }
+// coherent variant (ld.global, no .nc) for kernels that update the field they read
+template <typename T>
+__device__ __forceinline__ Spinor<T> load_spinor_c(const cplx<T>* p, size_t s) {
+    Spinor<T> r;
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.c0.x), "=d"(r.c0.y), "=d"(r.c1.x), "=d"(r.c1.y) : "l"(p + 2 * s));
+    } else {
+        float4 v = *(reinterpret_cast<const float4*>(p) + s);
+        r.c0 = make_float2(v.x, v.y); r.c1 = make_float2(v.z, v.w);
+    }
+    return r;
+}
 template <typename T>
 __device__ __forceinline__ void store_spinor(cplx<T>* __restrict__ p, size_t s, const Spinor<T>& v) {
     if constexpr (sizeof(T) == 8) {
@@ -130,6 +142,48 @@ wilson_march_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in,
     if (DOTS) grid_reduce<4, WX>(red, partials, counter, dots, blockIdx.x, gridDim.x);
 }
 
+// red-black Gauss-Seidel half sweep, matrix-free: phi(s) = (r(s) - hop(s)) / (2+m) on the sites with
+// (x + y + yoff) % 2 == colour (f_relax's update, S6/level.h:116-121, with D0 = (2+m) 1).  One thread per
+// updated site; a warp covers 64 consecutive x.  Traffic per full sweep (c128): phi 32+32, r 32, links 2x32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+wilson_rb_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ U,
+                 const cplx<T>* __restrict__ U_lo, const cplx<T>* __restrict__ r, T inv_diag, int Lx, int Ly,
+                 int colour, int yoff) {
+    using C = cplx<T>;
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    const T half = (T)0.5;
+    for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < S2; h += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(h / Lh);
+        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        const size_t row = (size_t)y * Lx, s = row + x;
+        const int xp = (x + 1 == Lx) ? 0 : x + 1, xm = (x == 0) ? Lx - 1 : x - 1;
+        const Spinor<T> qxp = load_spinor_c<T>(phi, row + xp), qxm = load_spinor_c<T>(phi, row + xm);
+        const Spinor<T> qyp = (y + 1 == Ly) ? load_spinor_c<T>(hi, x) : load_spinor_c<T>(phi, s + Lx);
+        const Spinor<T> qym = (y == 0) ? load_spinor_c<T>(lo, x) : load_spinor_c<T>(phi, s - Lx);
+        const Spinor<T> lk = load_spinor<T>(U, s);
+        const C uxm = __ldg(U + 2 * (row + xm));
+        const C uym = (y == 0) ? __ldg(U_lo + 2 * (size_t)x + 1) : __ldg(U + 2 * (s - Lx) + 1);
+        const C A = cmul(lk.c0, csub(qxp.c0, qxp.c1));
+        const C B = cmulc(uxm, cadd(qxm.c0, qxm.c1));
+        const C Cc = cmul(lk.c1, cadd(qyp.c0, cmul_i(qyp.c1)));
+        const C Dd = cmulc(uym, csub(qym.c0, cmul_i(qym.c1)));
+        const C h0 = cadd(cadd(A, B), cadd(Cc, Dd));
+        const C h1 = cadd(csub(B, A), cmul_i(csub(Dd, Cc)));
+        Spinor<T> o;
+        if (r) {
+            const Spinor<T> rr = load_spinor<T>(r, s);
+            o.c0.x = (rr.c0.x - half * h0.x) * inv_diag; o.c0.y = (rr.c0.y - half * h0.y) * inv_diag;
+            o.c1.x = (rr.c1.x - half * h1.x) * inv_diag; o.c1.y = (rr.c1.y - half * h1.y) * inv_diag;
+        } else {
+            o.c0.x = -half * h0.x * inv_diag; o.c0.y = -half * h0.y * inv_diag;
+            o.c1.x = -half * h1.x * inv_diag; o.c1.y = -half * h1.y * inv_diag;
+        }
+        store_spinor<T>(phi, s, o);
+    }
+}
+
 // materialise D[s][5][n][n] (column-major blocks) for the level-0 operator
 template <typename T>
 __global__ void lvl0_matrix_kernel(cplx<T>* __restrict__ D, const cplx<T>* __restrict__ U,
@@ -214,4 +268,20 @@ extern "C" int mg2d_lvl0_matrix(mg2d_ctx* ctx, void* D, const void* U, const voi
     else if (dtype == MG2D_C64) lvl0_matrix_kernel<float><<<grid, 256, 0, st>>>((float2*)D, (const float2*)U, (const float2*)U_lo, (float)diag, wilson, Lx, Ly);
     else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_lvl0_matrix: bad dtype");
     return mg2d_check_launch(ctx, "mg2d_lvl0_matrix");
+}
+
+extern "C" int mg2d_wilson_relax_rb(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* U,
+                                    const void* U_lo, const void* r, double mass, int Lx, int Ly, int colour, int yoff,
+                                    int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !U || !U_lo || Lx < 2 || (Lx & 1) || Ly < 1 || (colour != 0 && colour != 1))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_relax_rb: bad argument (Lx must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long S2 = (long long)(Lx / 2) * Ly;
+    long long nb = (S2 + 255) / 256; if (nb > (long long)ctx->num_sms * 32) nb = (long long)ctx->num_sms * 32;
+    const double inv = 1.0 / (2.0 + mass);
+    if (dtype == MG2D_C128) wilson_rb_kernel<double><<<(int)nb, 256, 0, st>>>((double2*)phi, (const double2*)phi_lo, (const double2*)phi_hi, (const double2*)U, (const double2*)U_lo, (const double2*)r, inv, Lx, Ly, colour, yoff);
+    else if (dtype == MG2D_C64) wilson_rb_kernel<float><<<(int)nb, 256, 0, st>>>((float2*)phi, (const float2*)phi_lo, (const float2*)phi_hi, (const float2*)U, (const float2*)U_lo, (const float2*)r, (float)inv, Lx, Ly, colour, yoff);
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_relax_rb: bad dtype");
+    return mg2d_check_launch(ctx, "mg2d_wilson_relax_rb");
 }

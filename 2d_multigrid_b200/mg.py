@@ -195,6 +195,23 @@ class Level:
                 mg.allreduce(d[:4 * nvec])
                 mg.ctx.call("mg2d_mr_update", _ptr(phi), _ptr(res), _ptr(t), _ptr(d), float(mg.p.mr_omega),
                             vs, mg.dcode, nvec, vs, _stream())
+        elif smoother == "rbgs":
+            hs = vs
+            for _ in range(num_iter):
+                for colour in (0, 1):
+                    if self.matrix_free:
+                        u_lo = self.U.data_ptr() + (self.L - 1) * self.L * 2 * self.U.element_size()
+                        for v in range(nvec):
+                            ph = phi if nvec == 1 else phi[v]
+                            rv = None if r is None else (r if nvec == 1 else r[v])
+                            lo, hi = self._halo(ph)
+                            mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), u_lo, _ptr(rv),
+                                        float(mg.p.mass), self.L, self.L, colour, 0, mg.dcode, _stream())
+                    else:
+                        self._ensure_D0inv()
+                        lo, hi = self._halo(phi if nvec == 1 else phi[0])
+                        mg.ctx.call("mg2d_relax_rb", _ptr(phi), lo, hi, _ptr(self.D), _ptr(self.D0inv), _ptr(r),
+                                    self.n, self.L, self.L, colour, 0, mg.dcode, nvec, vs, hs, _stream())
         else:
             raise ValueError(smoother)
 
@@ -476,8 +493,54 @@ def MG_ntl(mg: MG):
     return a
 
 
+class CycleGraph:
+    """One multigrid cycle (f_MG_simple / f_MG_ntl) + the fused residual norm, captured into a CUDA graph so
+    that a cycle costs one launch on the host.  Smoothers 'gs' (cooperative wavefront kernel) stay eager."""
+
+    def __init__(self, mg: MG, with_resmag: bool = True):
+        self.mg = mg
+        self.ntl = mg.p.ntl and mg.p.nlevels > 0
+        self.with_resmag = with_resmag
+        self.graph = None
+        self.weights = None
+        self.enabled = mg.p.smoother != "gs"
+
+    def _body(self):
+        mg = self.mg
+        if self.ntl:
+            self.weights = MG_ntl(mg)
+        else:
+            MG_simple(mg)
+        if self.with_resmag:
+            mg.LVL[0].residue_mag_async()
+
+    def run(self):
+        if not self.enabled:
+            self._body()
+            return
+        if self.graph is None:
+            # warm-up on a side stream (allocates every lazily created work buffer), then capture
+            mg = self.mg
+            saved = [(lv, lv.phi.clone(), lv.r.clone()) for lv in mg.LVL]
+            saved += [(nt, nt.phi.clone(), nt.r.clone()) for row in mg.NTL for nt in row if nt.phi is not None and nt.r is not None]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for lv, ph, r in saved:
+                lv.phi.copy_(ph); lv.r.copy_(r)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            for lv, ph, r in saved:      # capture does not execute, but keep the state explicit
+                lv.phi.copy_(ph); lv.r.copy_(r)
+        self.graph.replay()
+
+
 def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, check_every: int = 1,
-               record_phi: bool = False):
+               record_phi: bool = False, use_graph: bool = False):
     """f_perform_MG (S6/modules_main.h:442-481): cycles until |r - D phi|/|r| < tol; diverged if > 1e6.
     The residual norms are produced on the device by the fused residual kernel; the host reads them every
     `check_every` cycles (1 = the reference's behaviour)."""
@@ -488,12 +551,23 @@ def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, c
     hist = torch.zeros((max(check_every, 1), 4), dtype=torch.float64, device=mg.device)
     whist = torch.zeros((max(check_every, 1), 8), dtype=torch.float64, device=mg.device)
     ntl = p.ntl and p.nlevels > 0
+    cyc = None
+    if use_graph:
+        cyc = mg.info.get("cycle_graph")
+        if cyc is None:
+            cyc = mg.info["cycle_graph"] = CycleGraph(mg)
     it = 0
     while it < max_iters:
         nb = min(check_every, max_iters - it)
         for k in range(nb):
             if record_phi:
                 info["phi_hist"].append(mg.LVL[0].phi.clone())
+            if cyc is not None:
+                cyc.run()
+                if ntl:
+                    whist[k].copy_(cyc.weights[:8])
+                hist[k].copy_(mg.LVL[0].dots("resmag")[:4])
+                continue
             if ntl:
                 a = MG_ntl(mg)
                 whist[k].copy_(a[:8])
@@ -517,4 +591,85 @@ def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, c
                 info["diverged"] = True
                 return info
         it += nb
+    return info
+
+
+def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, restart: int = 8, check_every: int = 1,
+           use_graph: bool = False):
+    """Flexible GCR(restart) around one multigrid cycle as preconditioner (mirrors oracle gcr_MG; the reference
+    itself only iterates the cycle stationarily).  On entry LVL[0].phi / LVL[0].r hold x0 / b; on exit the
+    solution is in LVL[0].phi.  All scalars (Gram-Schmidt coefficients, step lengths) stay on the device."""
+    p = mg.p
+    tol = p.tol if tol is None else tol
+    max_iters = p.max_iters if max_iters is None else max_iters
+    lv0 = mg.LVL[0]
+    vs = lv0.S * lv0.n
+    call, dc, st = mg.ctx.call, mg.dcode, _stream
+    x, b = lv0.work("gcr_x"), lv0.work("gcr_b")
+    r = lv0.work("gcr_r")
+    Z, W = lv0.work("gcr_Z", restart), lv0.work("gcr_W", restart)
+    sc = lv0.dots("gcr")            # [0:2] dot, [2:4] <w,r>, [8+j] |w_j|^2, [4] |r|^2, [5] |b|^2
+    call("mg2d_copy", _ptr(x), _ptr(lv0.phi), vs, dc, st())
+    call("mg2d_copy", _ptr(b), _ptr(lv0.r), vs, dc, st())
+    lv0._stencil(r, x, b, _lib.MODE_RESID, None)
+    call("mg2d_norm2", _ptr(b), vs, dc, _ptr(sc[5:]), st())
+    mg.allreduce(sc[5:6])
+    for lv in mg.LVL[1:]:
+        call("mg2d_zero", _ptr(lv.phi), lv.S * lv.n, dc, st())
+    cyc = None
+    if use_graph:
+        cyc = mg.info.get("precond_graph")
+        if cyc is None:
+            cyc = mg.info["precond_graph"] = CycleGraph(mg, with_resmag=False)
+    ntl = p.ntl and p.nlevels > 0
+    info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
+    hist = torch.zeros(max(check_every, 1), dtype=torch.float64, device=mg.device)
+    bn2 = None
+    it, slot = 0, 0
+    done = False
+    while it < max_iters and not done:
+        nb = min(check_every, max_iters - it)
+        for k in range(nb):
+            # z = M(r): the cycle works on (LVL[0].phi, LVL[0].r)
+            call("mg2d_zero", _ptr(lv0.phi), vs, dc, st())
+            call("mg2d_copy", _ptr(lv0.r), _ptr(r), vs, dc, st())
+            if cyc is not None:
+                cyc.run()
+            elif ntl:
+                MG_ntl(mg)
+            else:
+                MG_simple(mg)
+            z, w = Z[slot], W[slot]
+            call("mg2d_copy", _ptr(z), _ptr(lv0.phi), vs, dc, st())
+            lv0._stencil(w, z, None, _lib.MODE_APPLY, None)
+            for j in range(slot):
+                call("mg2d_cdot_batch", _ptr(W[j]), vs, 1, _ptr(w), vs, 1, vs, dc, _ptr(sc), st())
+                mg.allreduce(sc[0:2])
+                call("mg2d_axpy_ratio2", _ptr(w), _ptr(W[j]), _ptr(z), _ptr(Z[j]), _ptr(sc), _ptr(sc[8 + j:]), -1.0, vs, dc, st())
+            call("mg2d_norm2", _ptr(w), vs, dc, _ptr(sc[8 + slot:]), st())
+            call("mg2d_cdot_batch", _ptr(w), vs, 1, _ptr(r), vs, 1, vs, dc, _ptr(sc[2:]), st())
+            mg.allreduce(sc[2:4]); mg.allreduce(sc[8 + slot:9 + slot])
+            call("mg2d_axpy_ratio2", _ptr(x), _ptr(z), None, None, _ptr(sc[2:]), _ptr(sc[8 + slot:]), 1.0, vs, dc, st())
+            call("mg2d_axpy_ratio2", _ptr(r), _ptr(w), None, None, _ptr(sc[2:]), _ptr(sc[8 + slot:]), -1.0, vs, dc, st())
+            call("mg2d_norm2", _ptr(r), vs, dc, _ptr(sc[4:]), st())
+            mg.allreduce(sc[4:5])
+            hist[k:k + 1].copy_(sc[4:5])
+            slot += 1
+            if slot >= restart:
+                slot = 0
+        h = hist[:nb].cpu()
+        if bn2 is None:
+            bn2 = float(sc[5].item())
+        for k in range(nb):
+            resmag = math.sqrt(h[k].item()) / math.sqrt(bn2) if bn2 > 0 else float("nan")
+            info["resnorms"].append(resmag)
+            info["iters"] = it + k + 1
+            if resmag < tol:
+                info["converged"] = True; done = True; break
+            if resmag > 1e6 or math.isnan(resmag):
+                info["diverged"] = True; done = True; break
+        it += nb
+    call("mg2d_copy", _ptr(lv0.phi), _ptr(x), vs, dc, st())
+    call("mg2d_copy", _ptr(lv0.r), _ptr(b), vs, dc, st())
+    info["true_resnorm"] = lv0.get_residue_mag()
     return info

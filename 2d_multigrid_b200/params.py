@@ -20,6 +20,7 @@ class MGParams:
     block: int = 2                   # argv[3]: block_x = block_y
     n_smooth: int = 3                # argv[2] num_iters: smoother sweeps per visit
     smoother: str = "gs"             # 'gs' (gs_flag=1, S6/params.h:61) | 'jacobi' (gs_flag=0) | 'mr' (north_star)
+                                     # | 'rbgs' (red-black ordering of the GS update)
     ntl: bool = False                # argv[7] t_flag
     n_copies: int = 4                # argv[8]
     tol: float = 1.0e-13             # res_threshold, S6/params.h:67
@@ -42,8 +43,8 @@ class MGParams:
     def __post_init__(self):
         if self.stencil not in ("wilson", "laplace"):
             raise ValueError(f"Incorrect stencil: {self.stencil}. Need either 'laplace' or 'wilson'")
-        if self.smoother not in ("gs", "jacobi", "mr"):
-            raise ValueError("smoother must be 'gs', 'jacobi' or 'mr'")
+        if self.smoother not in ("gs", "jacobi", "mr", "rbgs"):
+            raise ValueError("smoother must be 'gs', 'jacobi', 'mr' or 'rbgs'")
         if self.dtype not in ("complex128", "complex64"):
             raise ValueError("dtype must be complex128 or complex64")
         if self.ntl and self.nlevels < 2:
@@ -63,9 +64,9 @@ class MGParams:
             self.size.append(self.size[-1] // self.block)
             self.n_dof.append(self.n_dof_scale)
         if self.matrix_free is None:
-            self.matrix_free = self.stencil == "wilson" and self.smoother == "mr"
-        if self.matrix_free and (self.stencil != "wilson" or self.smoother != "mr"):
-            raise ValueError("matrix_free needs stencil='wilson' and smoother='mr'")
+            self.matrix_free = self.stencil == "wilson" and self.smoother in ("mr", "rbgs")
+        if self.matrix_free and (self.stencil != "wilson" or self.smoother not in ("mr", "rbgs")):
+            raise ValueError("matrix_free needs stencil='wilson' and smoother 'mr' or 'rbgs'")
 
     @property
     def diag(self) -> float:

@@ -81,6 +81,17 @@ int mg2d_relax_jacobi(mg2d_ctx*, void* out, const void* in, const void* in_lo, c
 int mg2d_relax_gs(mg2d_ctx*, void* phi, const void* D, const void* D0inv, const void* r, int n, int L,
                   int num_iter, int dtype, int nvec, long long vstride, void* stream);
 
+/* Level::f_relax update rule in red-black (two-colour) ordering, one half sweep IN PLACE: the sites with
+ * (x + y + yoff) % 2 == colour are updated from the other colour (parallel stand-in for the sequential
+ * lexicographic order of S6/level.h:113-123; mirrored by oracle Level.relax_rb).  Lx even. */
+int mg2d_relax_rb(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* D, const void* D0inv,
+                  const void* r, int n, int Lx, int Ly, int colour, int yoff, int dtype, int nvec,
+                  long long vstride, long long hstride, void* stream);
+/* the same for the matrix-free level-0 Wilson operator (D0 = (2+m) 1) */
+int mg2d_wilson_relax_rb(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* U,
+                         const void* U_lo, const void* r, double mass, int Lx, int Ly, int colour, int yoff,
+                         int dtype, void* stream);
+
 /* ---- BLAS-1 style fused updates ------------------------------------------------------------------------ */
 /* MR smoother update: alpha = omega * <t,res>/<t,t> read from `dots` (as written by a stencil call with
  * in=res, out=t); phi += alpha res; res -= alpha t. */
@@ -89,6 +100,10 @@ int mg2d_mr_update(mg2d_ctx*, void* phi, void* res, const void* t, const double*
 /* y += a x, a = (a_re, a_im), or a read from device `a_dev` (2 doubles) when a_dev != NULL. */
 int mg2d_axpy(mg2d_ctx*, void* y, const void* x, double a_re, double a_im, const double* a_dev,
               long long nelem, int dtype, void* stream);
+/* y += sign*(num/den) x and (if y2) y2 += sign*(num/den) x2; num = 2 doubles (complex), den = 1 double, both on
+ * the device: the Gram-Schmidt and step updates of the outer GCR without a host round trip. */
+int mg2d_axpy_ratio2(mg2d_ctx*, void* y, const void* x, void* y2, const void* x2, const double* num,
+                     const double* den, double sign, long long nelem, int dtype, void* stream);
 int mg2d_zero(mg2d_ctx*, void* x, long long nelem, int dtype, void* stream);
 int mg2d_copy(mg2d_ctx*, void* dst, const void* src, long long nelem, int dtype, void* stream);
 /* dst = src converted between MG2D_C128 and MG2D_C64 */

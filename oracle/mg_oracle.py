@@ -61,7 +61,7 @@ class Params:
     max_iters: int = 50000    # S6/params.h:64
     res_threshold: float = 1.0e-13  # S6/params.h:67
     n_dof_scale: int | None = None  # dof on coarse levels: 4 (wilson) / 2 (laplace) (S6/params.h:75,81)
-    smoother: str | None = None     # None -> from gs_flag; 'gs' | 'jacobi' | 'mr' (mr: ours)
+    smoother: str | None = None     # None -> from gs_flag; 'gs' | 'jacobi' | 'mr' | 'rbgs' (mr, rbgs: ours)
     mr_omega: float = 1.0
     null_iters: int = 500     # S6/modules_main.h:193
     null_chunk: int = 4       # S6/level.h:190
@@ -330,9 +330,26 @@ class Level:
             self.phi += alpha * res
             res -= alpha * t
 
+    # red-black Gauss-Seidel (ours): the parallel ordering of f_relax's update rule; colour (x+y)%2 == 0
+    # first, then colour 1, each colour updated from the latest values of the other
+    def relax_rb(self, L: int, num_iter: int):
+        xp, xm, yp, ym = neighbours(L)
+        D, phi, r = self.D, self.phi, self.r
+        D0inv = -np.linalg.inv(D[:, 0])
+        s = np.arange(L * L)
+        par = ((s % L) + (s // L)) % 2
+        colours = [np.nonzero(par == c)[0] for c in (0, 1)]
+        for _ in range(num_iter):
+            for idx in colours:
+                acc = (mv(D[idx, 1], phi[xp[idx]]) + mv(D[idx, 2], phi[xm[idx]])
+                       + mv(D[idx, 3], phi[yp[idx]]) + mv(D[idx, 4], phi[ym[idx]]) - r[idx])
+                phi[idx] = mv(D0inv[idx], acc)
+
     def smooth(self, L: int, num_iter: int, p: Params):
         if p.smoother == "mr":
             self.relax_mr(L, num_iter, p.mr_omega)
+        elif p.smoother == "rbgs":
+            self.relax_rb(L, num_iter)
         else:
             self.relax(L, num_iter, 1 if p.smoother == "gs" else 0)
 
@@ -627,6 +644,57 @@ def perform_MG(LVL, NTL, p: Params, record_phi: bool = False):
             info["diverged"] = True
             break
     return info
+
+
+def gcr_MG(LVL, NTL, p: Params, b: np.ndarray, x0: np.ndarray | None = None, tol: float = 1e-10,
+           max_iters: int = 1000, restart: int = 8):
+    """Flexible GCR(restart) with one multigrid cycle (from a zero start) as the preconditioner (ours: the
+    reference only iterates the cycle stationarily, f_perform_MG).  Mirrored 1:1 by the CUDA driver.
+        z = M(r); w = D z; orthogonalise (w, z) against the stored (w_j, z_j) (modified Gram-Schmidt);
+        alpha = <w, r>/<w, w>; x += alpha z; r -= alpha w
+    Returns (x, info)."""
+    L0 = p.size[0]
+    lv0 = LVL[0]
+    x = np.zeros_like(b) if x0 is None else x0.copy()
+    lv0.phi, lv0.r = x, b
+    r = lv0.residue(L0)
+    bn = math.sqrt(np.sum(np.abs(b) ** 2))
+    Z, W = [], []
+    info = {"iters": 0, "resnorms": [], "converged": False, "diverged": False}
+    ntl = p.t_flag == 1 and p.nlevels > 0
+    for it in range(max_iters):
+        lv0.phi = np.zeros_like(b)
+        lv0.r = r.copy()
+        for lvl in range(1, p.nlevels + 1):
+            LVL[lvl].phi[:] = 0.0
+        if ntl:
+            MG_ntl(LVL, NTL, p)
+        else:
+            MG_simple(LVL, p)
+        z = lv0.phi
+        w = lv0.apply_D(z, L0)
+        for zj, wj, wjn in zip(Z, W, [np.sum(np.abs(wj) ** 2) for wj in W]):
+            beta = np.vdot(wj, w) / wjn
+            w = w - beta * wj
+            z = z - beta * zj
+        alpha = np.vdot(w, r) / np.sum(np.abs(w) ** 2)
+        x = x + alpha * z
+        r = r - alpha * w
+        Z.append(z)
+        W.append(w)
+        if len(Z) >= restart:
+            Z, W = [], []
+        resmag = math.sqrt(np.sum(np.abs(r) ** 2)) / bn
+        info["resnorms"].append(resmag)
+        info["iters"] = it + 1
+        if resmag < tol:
+            info["converged"] = True
+            break
+        if resmag > 1e6 or math.isnan(resmag):
+            info["diverged"] = True
+            break
+    lv0.phi, lv0.r = x, b
+    return x, info
 
 
 # --------------------------------------------------------------------------------------------------
