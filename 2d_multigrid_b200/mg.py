@@ -286,6 +286,13 @@ class MG:
         self.LVL = [Level(self, l) for l in range(params.nlevels + 1)]
         self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
         self.info = {}
+        self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
+
+    @property
+    def launches(self) -> int:
+        """Kernels of libmg2d_sm100.so launched so far (eager + replayed from graphs, minus capture-only)."""
+        cap = sum(g.nlaunch for g in self.info.values() if isinstance(g, CycleGraph))
+        return self.ctx.launches - cap + self.graph_launches
 
     def to_device(self, a) -> torch.Tensor:
         return torch.as_tensor(np.ascontiguousarray(a)).to(self.tdtype).to(self.device)
@@ -503,6 +510,7 @@ class CycleGraph:
         self.with_resmag = with_resmag
         self.graph = None
         self.weights = None
+        self.nlaunch = 0
         self.enabled = mg.p.smoother != "gs"
 
     def _body(self):
@@ -532,11 +540,14 @@ class CycleGraph:
             for lv, ph, r in saved:
                 lv.phi.copy_(ph); lv.r.copy_(r)
             self.graph = torch.cuda.CUDAGraph()
+            n0 = mg.ctx.launches
             with torch.cuda.graph(self.graph):
                 self._body()
+            self.nlaunch = mg.ctx.launches - n0
             for lv, ph, r in saved:      # capture does not execute, but keep the state explicit
                 lv.phi.copy_(ph); lv.r.copy_(r)
         self.graph.replay()
+        self.mg.graph_launches += self.nlaunch
 
 
 def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, check_every: int = 1,

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- 2D Wilson adaptive-MG time-to-solution (1e-10) and D-apply HBM GB/s on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (reference arm: the CPU path, see below)
+
+A "step" is one full solve of D x = b (point source, x0 = 0) to |r|/|b| < 1e-10 on the workload lattice with
+the hierarchy already set up and all inputs resident in HBM.  `value` is the time to solution in ms
+(higher_is_better = false); `e2e` is the same solve through the public API with the right-hand side in pinned
+HOST memory and the solution copied back to the host inside the timed region.
+
+Workload (config.workload): BASELINE.json configs[4]/[3] -- 2D U(1) Wilson, quenched beta=6 links generated on
+the device, mass = m_crit + 1e-3 (near-critical; m_crit located by MG inverse iteration), adaptive MG with
+8 null vectors per chirality-pair (16 coarse dof), 4x4 aggregates, levels L/4^k down to 16, red-black GS
+smoother (4 pre + 4 post), flexible GCR(8) outer iteration, complex128.
+
+Reference arm / cpu_baseline: the reference (single-threaded C++/Eigen) cannot be built for this workload --
+Eigen is absent and its coarse dof count is hard-wired to 4 -- so the CPU side is the numpy oracle port running
+the SAME algorithm on a bounded sample (a smaller lattice of the same hierarchy shape, a few outer iterations)
+and scaled per site and per iteration to the workload; the JSON says so in `sample`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOL = 1.0e-10
+METRIC = "wilson_mg_time_to_solution_1e-10"
+UNIT = "ms"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def workload_params(mg2d, L, mass, **kw):
+    nlevels = max(1, int(round(math.log(L / 16, 4))))
+    return mg2d.make_params(L, mass, nlevels=nlevels, block=4, n_null=8, n_smooth=4, smoother="rbgs", null_iters=100,
+                            tol=TOL, max_iters=500, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def oracle_sample(L_cpu: int, iters_cap: int, seed_delta: float = 1e-3):
+    """The numpy oracle on a bounded sample of the workload: same hierarchy shape (block 4, 16 coarse dof,
+    rbgs 4+4, GCR(8)), lattice L_cpu, at most iters_cap outer iterations.  Returns seconds per (site*iteration),
+    setup seconds per site, iterations done."""
+    import numpy as np
+    from oracle import mg_oracle as O
+    nlevels = max(1, int(round(math.log(L_cpu / 16, 4))))
+    th = O.gauge_quenched_phases(L_cpu, 6.0, sweeps=20, seed=1234)
+    U = O.gauge_from_phases(th)
+    po = O.Params(L=L_cpu, num_iters=4, block=4, m=-0.05, nlevels=nlevels, stencil="wilson", smoother="rbgs",
+                  n_dof_scale=16, null_iters=20)
+    t0 = time.perf_counter()
+    LVL, NTL = O.build_reference_problem(po, U)
+    O.compute_near_null(LVL, NTL, po, 1)
+    t_setup = time.perf_counter() - t0
+    b = np.zeros((L_cpu * L_cpu, 2), dtype=complex)
+    b[L_cpu // 2 + (L_cpu // 2) * L_cpu, 0] = 1.0
+    t0 = time.perf_counter()
+    _, info = O.gcr_MG(LVL, NTL, po, b, tol=TOL, max_iters=iters_cap, restart=8)
+    t_solve = time.perf_counter() - t0
+    return t_solve / (info["iters"] * L_cpu * L_cpu), t_setup / (L_cpu * L_cpu), info["iters"], t_solve
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU path (oracle port, see module docstring) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = args.L
+    Lc = 128
+    import numpy as np  # noqa: F401
+    cores = os.cpu_count() or 1
+    iters_gpu = args.ref_iters
+    vals = []
+    for _ in range(args.warmup):
+        oracle_sample(Lc, 2)
+    for _ in range(args.steps):
+        per_site_iter, _, it_done, t = oracle_sample(Lc, 3)
+        vals.append(per_site_iter * L * L * iters_gpu * 1e3)
+    v = sum(vals) / len(vals)
+    sample = (f"numpy oracle port, {Lc}^2 lattice with the workload's hierarchy shape (block 4, 16 coarse dof, rbgs 4+4, "
+              f"GCR(8)), 3 outer iterations timed; scaled per site and per iteration to {L}^2 x {iters_gpu} iterations "
+              f"(extrapolated; numpy/BLAS may use up to {cores} threads)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic",
+            "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "tol": TOL},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def time_kernel(fn, reps, flush=None):
+    import torch
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.add_(1.0)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--L", type=int, default=4096)
+    ap.add_argument("--delta", type=float, default=1e-3, help="mass offset above the estimated critical mass")
+    ap.add_argument("--ref-iters", type=int, default=20, help="outer iterations assumed by the reference arm's scaling")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra solve (+ one D-apply) with cudaProfilerStart/Stop for `ncu --profile-from-start off`; "
+                         "numbers printed by such a run are not bench values")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import mg2d
+    from importlib import import_module
+    critical = import_module("2d_multigrid_b200.critical")
+    dist_mod = import_module("2d_multigrid_b200.dist")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = dist_mod.init(world, rank, local) if world > 1 else None
+    L = args.L
+    pk, pk_src = peaks()
+
+    # ---- inputs (not timed): links, critical mass, hierarchy ---------------------------------------------
+    t0 = time.time()
+    th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=60, seed=1234, device=str(dev))
+    U = torch.exp(1j * th).to(torch.complex128)
+    del th
+    plaq = mg2d.gauge.plaquette(U, L).real
+    if rank == 0:
+        print(f"# links {L}^2 beta=6 plaquette {plaq:.4f} ({time.time()-t0:.1f}s)", file=sys.stderr)
+    t0 = time.time()
+    if comm is None:
+        mcrit, _ = critical.estimate_critical_mass(U, lambda m: workload_params(mg2d, L, m), iters=4, refine=3)
+    else:
+        mcrit = dist_mod.bcast_float(comm, critical.estimate_critical_mass(
+            U, lambda m: workload_params(mg2d, L, m), iters=4, refine=3)[0] if rank == 0 else 0.0)
+    mass = mcrit + args.delta
+    torch.cuda.synchronize()
+    t_crit = time.time() - t0
+    p = workload_params(mg2d, L, mass)
+    t0 = time.time()
+    mg = mg2d.setup(U, p, init="device") if comm is None else dist_mod.setup(U, p, comm)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t0
+    if rank == 0:
+        print(f"# m_crit~{mcrit:.5f} ({t_crit:.1f}s)  mass {mass:.5f}  setup {t_setup:.2f}s levels {p.size} dof {p.n_dof}", file=sys.stderr)
+
+    lv0 = mg.LVL[0]
+    rhs_host = torch.zeros((L * L, 2), dtype=torch.complex128).pin_memory()
+    rhs_host[L // 2 + (L // 2) * L, 0] = 1.0
+    rhs = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev)
+    x_host = torch.empty((L * L, 2), dtype=torch.complex128).pin_memory()
+
+    def barrier():
+        if comm is not None:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def one_solve():
+        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4)
+
+    # ---- device-resident steps ------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        x, info = one_solve()
+    barrier()
+    n0 = mg.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        x, info = one_solve()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    launches = mg.launches - n0
+    if comm is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one_solve()
+        tmp_a, tmp_b = lv0.new_field(), lv0.new_field()
+        lv0.apply_D(tmp_b, tmp_a)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        del tmp_a, tmp_b
+
+    # ---- end to end: host rhs -> H2D -> solve -> D2H solution -----------------------------------------------
+    def e2e_solve():
+        r = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev, non_blocking=True)
+        xx, inf = mg2d.solve(mg, rhs=r, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4)
+        if comm is not None:
+            mg.gather_field(xx, x_host)
+        else:
+            x_host.copy_(xx, non_blocking=True)
+        torch.cuda.synchronize()
+        return inf
+    e2e_solve()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_solve()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if comm is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    nbytes = L * L * 2 * 16
+
+    if rank != 0:
+        return
+
+    # ---- per-kernel rooflines (rank 0, local data; inputs >> L2 or L2 flushed) -----------------------------
+    flush = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # 256 MiB > 126 MB L2
+    hbm = float(pk["hbm_gbs"])
+    kern = []
+    a, b_ = lv0.new_field(), lv0.new_field()
+    a.normal_()
+    S0 = lv0.S
+    t_apply = time_kernel(lambda: lv0.apply_D(b_, a), 20, flush)
+    kern.append(("wilson_march_kernel<double> (D-apply, matrix-free)", 96.0 * S0, t_apply))
+    lv0.phi.copy_(a)
+    t_rb0 = time_kernel(lambda: lv0.relax(1, smoother="rbgs"), 10, flush)
+    kern.append(("wilson_rb_kernel<double> x2 (one red-black GS sweep, level 0)", 160.0 * S0, t_rb0))
+    if p.nlevels >= 1:
+        l1 = mg.LVL[1]
+        n1 = l1.n
+        t_rb1 = time_kernel(lambda: l1.relax(1, smoother="rbgs"), 10, flush if l1.S * n1 * n1 * 96 < 2e8 else None)
+        kern.append((f"stencil_rb_kernel<double,{n1}> x2 (one red-black GS sweep, level 1)", (4 * n1 * n1 + n1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
+        c, d_ = l1.new_field(), l1.new_field()
+        c.normal_()
+        t_ap1 = time_kernel(lambda: l1.apply_D(d_, c), 10, flush if l1.S * n1 * n1 * 80 < 2e8 else None)
+        kern.append((f"stencil_kernel<double,{n1}> (coarse D-apply, level 1)", (5 * n1 * n1 + 2 * n1) * 16.0 * l1.S, t_ap1))
+        t_res = time_kernel(lambda: lv0.restriction(l1.r, a, 1), 10, flush)
+        kern.append((f"restrict_kernel<double,2,{n1}> (level 0->1)", ((n1 * 2 + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
+        t_pro = time_kernel(lambda: lv0.prolongation(b_, l1.phi, 1), 10, flush)
+        kern.append((f"prolong_kernel<double,2,{n1}> (level 1->0)", ((n1 * 2 + 2 * 2) * 16.0 + n1 * 16.0 / 16) * S0, t_pro))
+    table = [{"kernel": k, "bytes": by, "ms": t, "gbs": by / t / 1e6, "frac": by / t / 1e6 / hbm} for k, by, t in kern]
+    # share of one V-cycle (nu = 4 pre + 4 post sweeps per level) taken by the level-1 smoother, from these timings
+    dom = max(table[1:3], key=lambda r: r["ms"]) if len(table) > 2 else table[0]
+    dapply = table[0]
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = None
+    if os.path.exists(traffic_file):
+        try:
+            traffic = json.load(open(traffic_file)).get(dom["kernel"].split(" ")[0])
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded oracle sample, scaled ----------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        Lc = 128
+        per_site_iter, setup_per_site, it_done, t_cpu = oracle_sample(Lc, 3)
+        cpu = {"value": per_site_iter * L * L * info["iters"] * 1e3, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": (f"numpy oracle port, same algorithm on a {Lc}^2 lattice (block 4, 16 coarse dof, rbgs 4+4, GCR(8)), "
+                          f"{it_done} outer iterations in {t_cpu:.1f}s; scaled per site x iteration to {L}^2 x {info['iters']} "
+                          f"iterations (extrapolated)")}
+
+    line = {
+        "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic",
+        "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "plaquette": plaq, "mass": mass,
+                   "m_crit_est": mcrit, "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
+                   "smoother": "rbgs 4+4", "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
+                   "final_true_residual": info.get("true_resnorm"), "converged": info["converged"],
+                   "setup_s": t_setup, "mcrit_s": t_crit, "cache": "working set >> L2 (126 MB); kernel timings flush L2 with a 256 MiB write",
+                   "parallelism": f"strip{world}"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+        "gpu_launches": launches,
+        "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s",
+                     "frac": dom["frac"], "traffic": traffic, "peak_source": pk_src},
+        "dapply": {"kernel": dapply["kernel"], "bound": "hbm", "achieved": dapply["gbs"], "peak": hbm, "unit": "GB/s",
+                   "frac": dapply["frac"], "bytes_per_site": 96, "us": dapply["ms"] * 1e3, "target_frac": 0.70},
+        "kernels": table,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/mg2d.h
+declares (no compute call is made), the ctypes table matches the header, and the host-side parameter logic
+follows S6/params.h."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import mg2d
+from mg2d import _lib
+
+
+def _header_functions(repo_root):
+    txt = open(os.path.join(repo_root, "include", "mg2d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mg2d_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(repo_root):
+    names = _header_functions(repo_root)
+    assert len(names) >= 35
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail("libmg2d_sm100.so is not built: run __graft_entry__.build()")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.mg2d_version() >= 100
+
+
+def test_ctypes_table_matches_header(repo_root):
+    names = set(_header_functions(repo_root))
+    bound = set(_lib.SIGNATURES) | set(_lib.PLAIN)
+    assert names == bound, names ^ bound
+    # argument counts agree with the prototypes
+    txt = open(os.path.join(repo_root, "include", "mg2d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for name, args in _lib.SIGNATURES.items():
+        proto = re.search(name + r"\s*\((.*?)\)\s*;", txt, flags=re.S).group(1)
+        assert len(proto.split(",")) == len(args) + 1, name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mg2d.MG2DError):
+        mg2d.MG(mg2d.make_params(16, 0.1))
+    with pytest.raises(mg2d.MG2DError):
+        mg2d.ScalarMG(16, 0.1, 1)
+
+
+def test_params_follow_reference():
+    p = mg2d.make_params(64, -0.015, nlevels=3, block=2)
+    assert p.size == [64, 32, 16, 8] and p.n_dof == [2, 4, 4, 4]           # S6/params.h:75,115,121
+    assert abs(p.diag - (2.0 - 0.015)) < 1e-15                              # 1/scale[0], S6/params.h:76
+    q = mg2d.make_params(32, 0.1, stencil="laplace", nlevels=2)
+    assert q.n_dof == [1, 2, 2] and abs(q.diag + 4.1) < 1e-15               # S6/params.h:81-82, level.h:148
+    c4 = mg2d.make_params(1024, 0.0, nlevels=4, block=4, n_null=8, smoother="rbgs")
+    assert c4.size == [1024, 256, 64, 16, 4] and c4.n_dof == [2, 16, 16, 16, 16] and c4.matrix_free
+    with pytest.raises(ValueError):
+        mg2d.make_params(16, 0.1, nlevels=1, ntl=True)                      # S6/params.h:52-55
+    with pytest.raises(ValueError):
+        mg2d.make_params(16, 0.1, nlevels=5)                                # S6/params.h:100-106
+    with pytest.raises(ValueError):
+        mg2d.make_params(16, 0.1, stencil="staggered")                      # S6/params.h:84-86
+    a = mg2d.from_argv(["32", "3", "2", "1", "-0.015", "4", "1", "4"])      # S6/params.h:42-50
+    assert (a.L, a.n_smooth, a.block, a.mass, a.nlevels, a.ntl, a.n_copies) == (32, 3, 2, -0.015, 4, True, 4)
+
+
+def test_rng_product_copy_matches_oracle():
+    import numpy as np
+    from oracle import mg_oracle as O
+    assert np.array_equal(mg2d.StdMT19937(7).uniform_pm_pi(64), O.StdMT19937(7).uniform_pm_pi(64))
+
+
+def test_phase_file_roundtrip(tmp_path):
+    import numpy as np
+    L = 6
+    th = np.random.default_rng(0).uniform(-3, 3, (L * L, 2))
+    f = tmp_path / "phase_6_b6.0.dat"
+    mg2d.gauge.write_phase_file(str(f), th, L)
+    assert np.allclose(mg2d.gauge.read_phase_file(str(f), L), th, atol=1e-15)
+    lines = open(f).read().split()
+    # x outer, y inner, dir inner (S6/gauge.h:103-107): second record is (x=0,y=0,dir=1), third (x=0,y=1,dir=0)
+    assert abs(float(lines[1]) - th[0, 1]) < 1e-15 and abs(float(lines[2]) - th[L, 0]) < 1e-15

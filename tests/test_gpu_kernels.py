@@ -1,0 +1,245 @@
+"""GPU parity tests proper: every kernel behind the C ABI against the numpy oracle on identical seeded inputs.
+fp64 tolerance: 1e-12 relative (BASELINE.json north_star: "D.x within 1e-12 relative (fp64)"); complex64
+variants 2e-5."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import mg2d
+from oracle import mg_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def crand(rng, *s):
+    return rng.normal(size=s) + 1j * rng.normal(size=s)
+
+
+def _pair(L, m, stencil="wilson", nlevels=2, block=2, n_null=None, **kw):
+    """oracle levels + GPU MG with identical reference-compatible initial data."""
+    nds = None if n_null is None else (2 * n_null if stencil == "wilson" else n_null)
+    po = O.Params(L=L, num_iters=2, block=block, m=m, nlevels=nlevels, stencil=stencil, n_dof_scale=nds, null_iters=24, **kw)
+    U = O.gauge_gaussian(L, width=0.4, seed=9)
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    p = mg2d.make_params(L, m, stencil=stencil, nlevels=nlevels, block=block, n_null=n_null, n_smooth=2, null_iters=24,
+                         ntl=bool(kw.get("t_flag", 0)), n_copies=kw.get("n_copies", 4), matrix_free=False)
+    mg = mg2d.MG(p)
+    mg.init_reference_fields()
+    mg.set_gauge(T(U))
+    return po, LVLo, NTLo, p, mg, U
+
+
+@pytest.mark.parametrize("L", [4, 6, 34, 64, 130, 256])
+def test_wilson_apply_matrix_free(L):
+    """mg2d_wilson_apply vs Level.apply_D; ragged sizes exercise the partial-warp / partial-strip paths."""
+    rng = np.random.default_rng(L)
+    po, LVLo, _, p, mg, U = _pair(L, -0.03, nlevels=1)
+    v = crand(rng, L * L, 2)
+    want = LVLo[0].apply_D(v, L)
+    lv = mg.LVL[0]
+    lv.matrix_free = True
+    out = torch.empty_like(T(v))
+    lv.apply_D(out, T(v))
+    assert rel(out, want) < TOL
+    # residual + fused reductions
+    d = lv.dots("t")
+    lv.phi.copy_(T(v))
+    lv._stencil(out, lv.phi, lv.r, 1, d)
+    r_want = LVLo[0].r - want
+    assert rel(out, r_want) < TOL
+    dd = d[:4].cpu().numpy()
+    assert abs(dd[0] / np.sum(np.abs(r_want) ** 2) - 1) < TOL
+    assert abs((dd[1] + 1j * dd[2]) / np.vdot(r_want, v) - 1) < 1e-10
+    assert abs(dd[3] / np.sum(np.abs(LVLo[0].r) ** 2) - 1) < TOL
+
+
+def test_wilson_apply_complex64():
+    L = 64
+    rng = np.random.default_rng(1)
+    po, LVLo, _, _, _, U = _pair(L, 0.01, nlevels=1)
+    p = mg2d.make_params(L, 0.01, nlevels=1, dtype="complex64", matrix_free=False)
+    mg = mg2d.MG(p)
+    mg.init_reference_fields()
+    mg.set_gauge(T(U))
+    v = crand(rng, L * L, 2)
+    want = LVLo[0].apply_D(v, L)
+    out = torch.empty((L * L, 2), dtype=torch.complex64, device="cuda")
+    mg.LVL[0].apply_D(out, T(v).to(torch.complex64))
+    assert rel(out, want) < 2e-5
+    mg.LVL[0].matrix_free = True
+    mg.LVL[0].apply_D(out, T(v).to(torch.complex64))
+    assert rel(out, want) < 2e-5
+
+
+@pytest.mark.parametrize("stencil", ["wilson", "laplace"])
+def test_lvl0_matrix_and_stencil(stencil):
+    L = 12
+    rng = np.random.default_rng(2)
+    po, LVLo, _, p, mg, U = _pair(L, 0.05, stencil=stencil, nlevels=1)
+    assert rel(mg2d.D_to_reference_layout(mg.LVL[0].D), LVLo[0].D) < 1e-15
+    n = po.n_dof[0]
+    v = crand(rng, L * L, n)
+    out = torch.empty_like(T(v))
+    mg.LVL[0].apply_D(out, T(v))
+    assert rel(out, LVLo[0].apply_D(v, L)) < TOL
+    assert abs(mg.LVL[0].get_residue_mag() / LVLo[0].get_residue_mag(L) - 1) < TOL
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32])
+def test_block_stencil_all_sizes(n):
+    """generic n x n block stencil: apply, residual, D0 inverse, Jacobi, lexicographic GS, red-black GS."""
+    L = 10
+    rng = np.random.default_rng(n)
+    S = L * L
+    Dref = crand(rng, S, 5, n, n) * 0.2
+    Dref[:, 0] += 3.0 * np.eye(n)
+    lvo = O.Level()
+    lvo.D, lvo.phi, lvo.r = Dref, crand(rng, S, n), crand(rng, S, n)
+    p = mg2d.make_params(L, 0.1, nlevels=0, matrix_free=False)
+    mg = mg2d.MG(p)
+    lv = mg.LVL[0]
+    lv.n, lv.L, lv.S = n, L, S
+    lv.D = mg2d.D_to_reference_layout(T(Dref))
+    lv.phi, lv.r = T(lvo.phi), T(lvo.r)
+    v = crand(rng, S, n)
+    out = torch.empty_like(T(v))
+    lv.apply_D(out, T(v))
+    assert rel(out, lvo.apply_D(v, L)) < TOL
+    rt = torch.empty_like(out)
+    lv.residue(rt)
+    assert rel(rt, lvo.residue(L)) < TOL
+    lv._ensure_D0inv()
+    assert rel(lv.D0inv.transpose(-1, -2), np.linalg.inv(Dref[:, 0])) < 1e-11
+    for sm, fn in (("jacobi", lambda o: o.relax(L, 2, 0)), ("gs", lambda o: o.relax(L, 2, 1)), ("rbgs", lambda o: o.relax_rb(L, 2)),
+                   ("mr", lambda o: o.relax_mr(L, 2))):
+        o2 = copy.deepcopy(lvo)
+        fn(o2)
+        phi0 = lv.phi.clone()
+        lv.relax(2, smoother=sm)
+        assert rel(lv.phi, o2.phi) < 1e-11, sm
+        lv.phi.copy_(phi0)
+
+
+def test_relax_matrix_free_and_batched():
+    L = 16
+    po, LVLo, _, p, mg, U = _pair(L, 0.02, nlevels=1)
+    lv = mg.LVL[0]
+    for sm, fn in (("rbgs", lambda o: o.relax_rb(L, 3)), ("mr", lambda o: o.relax_mr(L, 3))):
+        o2 = copy.deepcopy(LVLo[0])
+        fn(o2)
+        for mf in (False, True):
+            lv.matrix_free = mf
+            phi0 = lv.phi.clone()
+            lv.relax(3, smoother=sm)
+            assert rel(lv.phi, o2.phi) < 1e-11, (sm, mf)
+            lv.phi.copy_(phi0)
+    lv.matrix_free = False
+    # batched vectors with r = 0 (near-null relaxation) equal one-at-a-time relaxation
+    rng = np.random.default_rng(3)
+    V = T(crand(rng, 3, L * L, 2))
+    for sm in ("gs", "jacobi", "rbgs", "mr"):
+        Vb = V.clone()
+        lv.relax(2, phi=Vb, r=None, smoother=sm)
+        for k in range(3):
+            o2 = copy.deepcopy(LVLo[0])
+            o2.phi, o2.r = V[k].cpu().numpy().copy(), np.zeros((L * L, 2), dtype=complex)
+            {"gs": lambda: o2.relax(L, 2, 1), "jacobi": lambda: o2.relax(L, 2, 0), "rbgs": lambda: o2.relax_rb(L, 2),
+             "mr": lambda: o2.relax_mr(L, 2)}[sm]()
+            assert rel(Vb[k], o2.phi) < 1e-11, (sm, k)
+
+
+@pytest.mark.parametrize("stencil,block,n_null", [("wilson", 2, None), ("laplace", 2, None), ("wilson", 4, 8), ("wilson", 2, 4), ("laplace", 4, 4)])
+def test_setup_and_transfer(stencil, block, n_null):
+    """near_null, norm_nn, ortho x2, check_ortho, coarse matrix, restrict / prolong (all quadrants) and the
+    reference's tests 1 (P P^dagger = 1) and 2 (Galerkin identity) evaluated on GPU data."""
+    L = 16
+    rng = np.random.default_rng(4)
+    po, LVLo, NTLo, p, mg, U = _pair(L, 0.05, stencil=stencil, nlevels=2 if block == 2 else 1, block=block, n_null=n_null)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    mg2d.compute_near_null(mg)
+    assert max(mg.info["ortho_worst"]) < TOL                              # f_check_ortho, S6/near_null.h:205
+    for l in range(po.nlevels):
+        assert rel(mg.LVL[l].phi_null, LVLo[l].phi_null) < 1e-10
+        assert rel(mg2d.D_to_reference_layout(mg.LVL[l + 1].D), LVLo[l + 1].D) < 1e-10
+        nf, nc = po.n_dof[l], po.n_dof[l + 1]
+        Sf, Sc = po.size[l] ** 2, po.size[l + 1] ** 2
+        vf, vc = crand(rng, Sf, nf), crand(rng, Sc, nc)
+        for quad in (1, 2, 3, 4):
+            rc = torch.empty_like(T(vc))
+            mg.LVL[l].restriction(rc, T(vf), quad)
+            assert rel(rc, LVLo[l].restriction(vf, l, po, quad)) < TOL
+            fo = vf.copy()
+            LVLo[l].prolongation(fo, vc, l + 1, po, quad)
+            fg = T(vf).clone()
+            cg = T(vc).clone()
+            mg.LVL[l].prolongation(fg, cg, quad, zero_vc=True)
+            assert rel(fg, fo) < TOL and float(cg.abs().max()) == 0.0
+        # test1 / test2 of S6/tests.h on the GPU
+        f1 = torch.zeros((Sf, nf), dtype=torch.complex128, device="cuda")
+        mg.LVL[l].prolongation(f1, T(vc), 1)
+        c1 = torch.empty_like(T(vc))
+        mg.LVL[l].restriction(c1, f1, 1)
+        assert float((c1 - T(vc)).abs().max()) < 1e-12
+        f2 = torch.empty_like(f1)
+        mg.LVL[l].apply_D(f2, f1)
+        mg.LVL[l].restriction(c1, f2, 1)
+        c2 = torch.empty_like(c1)
+        mg.LVL[l + 1].apply_D(c2, T(vc))
+        assert float((c1 - c2).abs().max()) < 1e-11
+
+
+def test_minres_pieces():
+    """Gram matrix (mg2d_cdot_batch), column-pivoted QR solve (mg2d_minres_solve), f_scale_phi."""
+    rng = np.random.default_rng(6)
+    p = mg2d.make_params(8, 0.1, nlevels=0, matrix_free=False)
+    mg = mg2d.MG(p)
+    n = 300
+    X, Y = crand(rng, 4, n), crand(rng, 3, n)
+    out = torch.zeros(64, dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    Xd, Yd = T(X), T(Y)          # keep the device tensors alive across the asynchronous call
+    mg.ctx.call("mg2d_cdot_batch", Xd.data_ptr(), n, 4, Yd.data_ptr(), n, 3, n, 0, out.data_ptr(), s)
+    got = out[:24].cpu().numpy()
+    want = np.conj(X) @ Y.T
+    assert np.max(np.abs((got[0::2] + 1j * got[1::2]).reshape(4, 3) - want)) < 1e-11
+    for k in (1, 2, 3, 4):
+        A, b = crand(rng, k, k), crand(rng, k)
+        g = T(np.stack([A.real, A.imag], -1).reshape(-1))
+        sv = T(np.stack([b.real, b.imag], -1).reshape(-1))
+        a = torch.zeros(8, dtype=torch.float64, device="cuda")
+        mg.ctx.call("mg2d_minres_solve", g.data_ptr(), sv.data_ptr(), k, a.data_ptr(), s)
+        av = a.cpu().numpy()
+        assert np.max(np.abs(av[0:2 * k:2] + 1j * av[1:2 * k:2] - O.colpiv_householder_qr_solve(A, b))) < 1e-11
+
+
+def test_error_behaviour():
+    """The ABI reports errors by return code + message; the python layer raises MG2DError (no exit(), no crash)."""
+    p = mg2d.make_params(8, 0.1, nlevels=1, matrix_free=False)
+    mg = mg2d.MG(p)
+    mg.init_reference_fields()
+    mg.set_gauge(T(O.gauge_cold(8)))
+    v = mg.LVL[0].new_field()
+    with pytest.raises(ValueError):
+        mg.LVL[0].apply_D(v, v)                                         # aliasing
+    s = torch.cuda.current_stream().cuda_stream
+    with pytest.raises(mg2d.MG2DError, match="n_dof"):
+        mg.ctx.call("mg2d_stencil_apply", v.data_ptr(), mg.LVL[0].phi.data_ptr(), v.data_ptr(), v.data_ptr(),
+                    mg.LVL[0].D.data_ptr(), None, 3, 8, 8, 0, 0, 1, 128, 128, None, s)
+    with pytest.raises(mg2d.MG2DError, match="geometry"):
+        mg.ctx.call("mg2d_restrict", v.data_ptr(), v.data_ptr(), v.data_ptr(), 2, 4, 9, 9, 2, 1, 0, s)
+    with pytest.raises(mg2d.MG2DError):
+        mg.ctx.call("mg2d_wilson_apply", None, v.data_ptr(), v.data_ptr(), v.data_ptr(), v.data_ptr(), v.data_ptr(),
+                    None, 0.1, 8, 8, 0, 0, None, s)
+    assert mg.ctx.launches > 0

@@ -1,0 +1,213 @@
+"""End-to-end parity: the GPU solver against the oracle on the BASELINE configs -- identical outer iteration
+counts, residual histories, near-null vectors and solutions -- plus size-independent properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+import mg2d
+from oracle import mg_oracle as O
+from oracle import scalar_s2 as S2
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def hist_close(hg, ho, rtol=1e-7, floor=5e-15):
+    """Residual histories agree to rtol, down to the rounding floor of the residual itself: a relative norm of
+    1e-13 is only defined to ~eps/1e-13 ~ 1e-3 relative, i.e. ~1e-16 absolute."""
+    return all(abs(a - b) <= rtol * b + floor for a, b in zip(hg, ho))
+
+
+def _run_both(L, m, U, stencil="wilson", nlevels=2, n_smooth=3, smoother="gs", ntl=False, n_copies=4, null_iters=40,
+              max_iters=300, block=2, n_null=None, tol=1e-13, **kw):
+    nds = None if n_null is None else (2 * n_null if stencil == "wilson" else n_null)
+    po = O.Params(L=L, num_iters=n_smooth, block=block, m=m, nlevels=nlevels, stencil=stencil, smoother=smoother,
+                  t_flag=int(ntl), n_copies=n_copies, null_iters=null_iters, max_iters=max_iters, n_dof_scale=nds,
+                  res_threshold=tol)
+    LVLo, NTLo, io = O.run_reference_flow(po, U)
+    p = mg2d.make_params(L, m, stencil=stencil, nlevels=nlevels, block=block, n_null=n_null, n_smooth=n_smooth,
+                         smoother=smoother, ntl=ntl, n_copies=n_copies, null_iters=null_iters, max_iters=max_iters, tol=tol, **kw)
+    mg, ig = mg2d.run_reference_flow(p, T(U))
+    return LVLo, io, mg, ig
+
+
+# config 2: 2D U(1) Wilson 64x64, adaptive 3-level MG (levels 64/32/16), fp64, the reference's GS smoother
+def test_config2_wilson64_three_level_gs():
+    L = 64
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 32.0, sweeps=30))
+    LVLo, io, mg, ig = _run_both(L, 0.02, U, nlevels=2, smoother="gs", null_iters=60)
+    assert io["converged"] and ig["converged"]
+    assert ig["iters"] == io["iters"]                                   # identical outer iteration count
+    assert ig["resnorms"][-1] < 1e-13
+    assert hist_close(ig["resnorms"], io["resnorms"])
+    assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-9
+    for l in range(2):
+        assert rel(mg.LVL[l].phi_null, LVLo[l].phi_null) < 1e-8
+
+
+@pytest.mark.parametrize("smoother", ["jacobi", "rbgs", "mr"])
+def test_wilson32_other_smoothers(smoother):
+    L = 32
+    U = O.gauge_gaussian(L, 0.3)
+    LVLo, io, mg, ig = _run_both(L, 0.05, U, nlevels=2, smoother=smoother, n_smooth=3, max_iters=400)
+    assert ig["iters"] == io["iters"] and ig["converged"] == io["converged"]
+    assert hist_close(ig["resnorms"], io["resnorms"])
+
+
+def test_laplace32_gauged():
+    L = 32
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
+    LVLo, io, mg, ig = _run_both(L, 0.05, U, stencil="laplace", nlevels=2, smoother="gs")
+    assert ig["converged"] and ig["iters"] == io["iters"]
+    assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-9
+
+
+# config 3 (scaled to what the oracle finishes in seconds): non-telescoping cycle with min-res weights
+@pytest.mark.parametrize("stencil,n_copies", [("wilson", 4), ("wilson", 2), ("laplace", 4), ("wilson", 1)])
+def test_ntl_minres(stencil, n_copies):
+    L = 32
+    U = O.gauge_gaussian(L, 0.3)
+    LVLo, io, mg, ig = _run_both(L, 0.05, U, stencil=stencil, nlevels=3, smoother="gs", ntl=True, n_copies=n_copies)
+    assert ig["converged"] and ig["iters"] == io["iters"]
+    # the first cycles (before chaotic amplification of rounding) agree to high accuracy, weights included
+    for a, b in zip(ig["resnorms"][:5], io["resnorms"][:5]):
+        assert abs(a / b - 1) < 1e-8
+    assert np.max(np.abs(ig["ntl_weights"][0][:n_copies] - io["ntl_weights"][0][:n_copies])) < 1e-8
+
+
+# config 4 shape at a size the oracle can follow: 8 null vectors, 4x4 aggregates
+def test_config4_shape_small():
+    L = 64
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
+    LVLo, io, mg, ig = _run_both(L, 0.0, U, nlevels=2, block=4, n_null=8, smoother="rbgs", n_smooth=2, null_iters=40, tol=1e-10)
+    assert ig["converged"] and ig["iters"] == io["iters"]
+    assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-8
+
+
+def test_gcr_outer_and_graph():
+    L = 32
+    U = O.gauge_gaussian(L, 0.3)
+    b = np.zeros((L * L, 2), dtype=complex)
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    po = O.Params(L=L, num_iters=2, block=2, m=0.02, nlevels=2, null_iters=40, smoother="rbgs")
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=4)
+    p = mg2d.make_params(L, 0.02, nlevels=2, n_smooth=2, smoother="rbgs", null_iters=40)
+    mg = mg2d.setup(T(U), p)
+    for use_graph in (False, True):
+        x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=4, use_graph=use_graph, check_every=3)
+        assert ig["iters"] >= io["iters"] and ig["resnorms"][io["iters"] - 1] < 1e-10
+        assert all(r >= 1e-10 for r in ig["resnorms"][:io["iters"] - 1])          # same first crossing
+        assert ig["true_resnorm"] < 1e-10                                        # final TRUE residual
+        assert rel(x, xo) < 1e-6
+    # stationary cycle from a graph equals the eager cycle
+    m1 = mg2d.setup(T(U), p)
+    x1, i1 = mg2d.solve(m1)
+    m2 = mg2d.setup(T(U), p)
+    x2, i2 = mg2d.solve(m2, use_graph=True)
+    assert i1["iters"] == i2["iters"] and float((x1 - x2).abs().max()) < 1e-10
+
+
+def test_supplied_null_vectors_and_public_api():
+    """setup(U, params, null_vectors=...) and the per-function API of SURVEY 8(b)."""
+    L = 16
+    U = O.gauge_gaussian(L, 0.3)
+    po = O.Params(L=L, num_iters=2, block=2, m=0.05, nlevels=2, null_iters=24)
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    p = mg2d.make_params(L, 0.05, nlevels=2, n_smooth=2, null_iters=24, matrix_free=False)
+    mg = mg2d.setup(T(U), p, null_vectors=[T(LVLo[0].phi_null), T(LVLo[1].phi_null)])
+    for l in (1, 2):
+        assert rel(mg2d.D_to_reference_layout(mg.LVL[l].D), LVLo[l].D) < 1e-10
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(L * L, 2)) + 0j
+    out = torch.empty_like(T(v))
+    mg2d.apply_D(out, T(v), 0, mg)
+    assert rel(out, LVLo[0].apply_D(v, L)) < 1e-12
+    assert abs(mg2d.residue_mag(0, mg) / LVLo[0].get_residue_mag(L) - 1) < 1e-12
+    mg2d.relax(0, 2, mg, 1)
+    LVLo[0].relax(L, 2, 1)
+    assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-11
+    vc = torch.zeros((64, 4), dtype=torch.complex128, device="cuda")
+    mg2d.restriction(vc, mg.LVL[0].phi, 0, mg, 1)
+    assert rel(vc, LVLo[0].restriction(LVLo[0].phi, 0, po, 1)) < 1e-11
+
+
+# config 1: real scalar Laplace 32x32 (and the 64x64 golden sweep) on the GPU
+@pytest.mark.parametrize("args,want", [((32, 0.1, 1, 3, 0), None), ((32, 0.2, 2, 20, 0), None), ((64, 0.1, 3, 3, 0), 19),
+                                       ((64, 0.2, 4, 3, 0), 7), ((64, 0.08, 3, 3, 0), 29), ((64, 0.1, 3, 3, 1), None),
+                                       ((32, 0.3, 0, 4, 0), None), ((16, 0.3, 2, 2, 1), None)])
+def test_config1_scalar_laplace(args, want):
+    L, m, nl, ni, tf = args
+    it_o, phi_o, hist_o = S2.solve(L, m, nl, ni, tf)
+    it_g, phi_g, hist_g = mg2d.solve_scalar(L, m, nl, ni, tf)
+    assert it_g == it_o                                                 # identical iteration count
+    if want is not None:
+        assert it_g == want                                             # NB/2c...:587-598 golden numbers
+    assert rel(phi_g, phi_o) < 1e-12
+    assert abs(hist_g[0] / hist_o[0] - 1) < 1e-12
+
+
+# ---- full-size properties (no oracle run possible at these sizes) ----------------------------------------
+def test_fullsize_properties_1024():
+    """config 4 size: linearity and gamma5-hermiticity of the matrix-free D, P P^dagger = 1, Galerkin identity,
+    gauge covariance, and a solve that reaches 1e-10 (true residual)."""
+    L = 1024
+    th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=20, device="cuda")
+    U = torch.exp(1j * th).to(torch.complex128)
+    p = mg2d.make_params(L, -0.02, nlevels=4, block=4, n_null=8, n_smooth=4, smoother="rbgs", null_iters=60, tol=1e-10, max_iters=200)
+    mg = mg2d.setup(U, p, init="device")
+    lv = mg.LVL[0]
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64, device="cuda") + 1j * torch.randn(*s, generator=g, dtype=torch.float64, device="cuda")
+    v, w = rnd(L * L, 2), rnd(L * L, 2)
+    Dv, Dw, Dvw = torch.empty_like(v), torch.empty_like(v), torch.empty_like(v)
+    lv.apply_D(Dv, v); lv.apply_D(Dw, w)
+    comb = v * (0.3 - 0.7j) + w
+    lv.apply_D(Dvw, comb)
+    assert float((Dvw - (Dv * (0.3 - 0.7j) + Dw)).abs().max()) < 1e-11          # linearity
+    g5 = torch.tensor([1.0, -1.0], dtype=torch.complex128, device="cuda")
+    lhs = torch.vdot((g5 * Dv).reshape(-1), w.reshape(-1))                      # <g5 D v, w>
+    rhs = torch.vdot(v.reshape(-1), (g5 * Dw).reshape(-1))                      # <v, g5 D w>
+    assert abs(lhs - rhs) / abs(lhs) < 1e-12                                     # D^dagger = g5 D g5
+    # gauge covariance of the kernel
+    om = torch.exp(1j * torch.rand(L * L, generator=g, dtype=torch.float64, device="cuda") * 6.283)
+    omx = torch.roll(om.reshape(L, L), -1, 1).reshape(-1)
+    omy = torch.roll(om.reshape(L, L), -1, 0).reshape(-1)
+    U2 = torch.stack([om * U[:, 0] * omx.conj(), om * U[:, 1] * omy.conj()], 1).contiguous()
+    lv2 = mg2d.MG(mg2d.make_params(L, -0.02, nlevels=0, smoother="rbgs")).LVL[0]
+    lv2.U, lv2.matrix_free = U2, True
+    out2 = torch.empty_like(v)
+    lv2.apply_D(out2, om[:, None] * v)
+    assert float((out2 - om[:, None] * Dv).abs().max()) < 1e-11
+    # test1 / test2 on the two finest interfaces
+    for l in (0, 1):
+        a, bl = mg.LVL[l], mg.LVL[l + 1]
+        vc = rnd(bl.S, bl.n)
+        f1 = torch.zeros((a.S, a.n), dtype=torch.complex128, device="cuda")
+        a.prolongation(f1, vc, 1)
+        c1 = torch.empty_like(vc)
+        a.restriction(c1, f1, 1)
+        assert float((c1 - vc).abs().max()) < 1e-11
+        f2 = torch.empty_like(f1)
+        a.apply_D(f2, f1)
+        a.restriction(c1, f2, 1)
+        c2 = torch.empty_like(vc)
+        bl.apply_D(c2, vc)
+        assert float((c1 - c2).abs().max()) < 1e-10
+    rhs_ = torch.zeros((L * L, 2), dtype=torch.complex128, device="cuda")
+    rhs_[L // 2 + (L // 2) * L, 0] = 1.0
+    x, info = mg2d.solve(mg, rhs=rhs_, tol=1e-10, outer="gcr", use_graph=True, check_every=4)
+    assert info["converged"] and info["true_resnorm"] < 1e-10
+    chk = torch.empty_like(x)
+    lv.apply_D(chk, x)
+    assert float(torch.linalg.vector_norm(chk - rhs_)) < 1e-10
