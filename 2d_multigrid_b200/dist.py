@@ -1,6 +1,156 @@
-"""Multi-GPU strip decomposition (placeholder until the strip path lands)."""
+"""Multi-GPU domain decomposition: 1-D strips in y over torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+The reference is single-process (no MPI/NCCL anywhere); this is new.  Site index is
+s = x + y*L with x fastest (S6/level.h:69-75), so a strip of rows is contiguous and its two halo rows are
+contiguous messages:
+
+  * rank p owns rows [p*L/P, (p+1)*L/P) of every DISTRIBUTED level; before each stencil application / red-black
+    half sweep it sends its last row to rank p+1 (their `lo` halo) and its first row to rank p-1 (their `hi`
+    halo) -- one grouped ncclSend/ncclRecv pair per neighbour, periodic (rank 0 <-> P-1).  The kernels take the
+    halo rows as separate pointers (include/mg2d.h), so no padded copies of the fields exist.
+  * reductions (residual norms, MR / GCR coefficients, near-null norms) are 1-40 doubles: ncclAllReduce.
+  * aggregates never straddle a strip (rows per rank divisible by the block), so restriction, prolongation and
+    the per-aggregate orthonormalisation are communication-free; the Galerkin product needs one halo row of P.
+  * coarse-level agglomeration: once a level has fewer than `min_rows` rows per rank (halo latency would
+    dominate), it and all coarser levels are REPLICATED: the restricted residual strips are all-gathered and
+    every rank redundantly runs the (tiny) coarse part of the cycle, then prolongs from its own rows.  No
+    scatter, no idle ranks, bit-identical coarse fields on every rank.
+
+The exchange helpers work on CPU tensors with the gloo backend as well, which is how tests/ cover the N>1
+host logic without GPUs.
+"""
 from __future__ import annotations
 
+import os
 
-def init(world, rank, local):
-    raise NotImplementedError("multi-GPU strips not built yet")
+import torch
+import torch.distributed as dist
+
+from .mg import MG
+from .params import MGParams
+
+MIN_ROWS = int(os.environ.get("MG2D_MIN_ROWS", "32"))
+
+
+def plan_strips(p: MGParams, world: int, min_rows: int = MIN_ROWS):
+    """For every level: (distributed?, rows per rank).  Distribution stops at the first level that cannot be cut
+    into >= min_rows rows per rank in whole aggregates; that level and all coarser ones are replicated."""
+    plan, alive = [], True
+    for lvl, L in enumerate(p.size):
+        rows = L // world
+        ok = alive and L % world == 0 and rows >= min_rows and (lvl == p.nlevels or rows % p.block == 0)
+        alive = ok
+        plan.append((ok, rows if ok else L))
+    return plan
+
+
+class Comm:
+    def __init__(self, world: int, rank: int, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.prev, self.next = (rank - 1) % world, (rank + 1) % world
+        self._halo = {}
+        self.backend = dist.get_backend(group)
+
+    def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None):
+        """Returns (lo, hi): the row below local row 0 (last row of rank-1) and the row above the last local row
+        (first row of rank+1), periodic.  t: [Ly*Lx, width...] or a batch [nvec, Ly*Lx, width]."""
+        if nvec == 1:
+            first, last = t[:Lx], t[(Ly - 1) * Lx:Ly * Lx]
+        else:
+            first, last = t[:, :Lx].contiguous(), t[:, (Ly - 1) * Lx:Ly * Lx].contiguous()
+        k = (key, tuple(first.shape), first.dtype)
+        if k not in self._halo:
+            self._halo[k] = (torch.empty_like(first), torch.empty_like(first))
+        lo, hi = self._halo[k]
+        if self.backend == "nccl":
+            # order matters when prev == next (2 ranks): my last row is the peer's lo, my first row its hi
+            ops = [dist.P2POp(dist.isend, last, self.next, self.group), dist.P2POp(dist.isend, first, self.prev, self.group),
+                   dist.P2POp(dist.irecv, lo, self.prev, self.group), dist.P2POp(dist.irecv, hi, self.next, self.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        else:
+            reqs = [dist.isend(last.contiguous(), self.next, group=self.group, tag=1), dist.isend(first.contiguous(), self.prev, group=self.group, tag=2),
+                    dist.irecv(lo, self.prev, group=self.group, tag=1), dist.irecv(hi, self.next, group=self.group, tag=2)]
+            for req in reqs:
+                req.wait()
+        return lo, hi
+
+    def allreduce(self, t: torch.Tensor, op: str = "sum"):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
+
+    def allgather(self, full: torch.Tensor, strip: torch.Tensor):
+        """full = concatenation of every rank's strip in rank order (strips are contiguous row blocks)."""
+        dist.all_gather_into_tensor(full.reshape(-1), strip.reshape(-1).contiguous(), group=self.group) \
+            if self.backend == "nccl" else self._allgather_list(full, strip)
+
+    def _allgather_list(self, full, strip):
+        parts = [torch.empty_like(strip) for _ in range(self.world)]
+        dist.all_gather(parts, strip.contiguous(), group=self.group)
+        full.reshape(-1).copy_(torch.cat([q.reshape(-1) for q in parts]))
+
+
+class DistMG(MG):
+    """MG whose finest levels are strip-decomposed over the ranks of `comm` (see module docstring)."""
+
+    def __init__(self, params: MGParams, comm: Comm, device: int | None = None, min_rows: int = MIN_ROWS):
+        super().__init__(params, device)
+        self.comm = comm
+        if params.ntl:
+            raise NotImplementedError("the non-telescoping cycle shifts aggregates across strip boundaries: one GPU only")
+        self.plan = plan_strips(params, comm.world, min_rows)
+        if not self.plan[0][0]:
+            raise ValueError(f"lattice {params.L} cannot be cut into {comm.world} strips of >= {min_rows} rows in whole aggregates")
+        for lv, (d, rows) in zip(self.LVL, self.plan):
+            if d:
+                lv.set_strip(comm.rank * rows, rows)
+
+    # field movement between a full host/device field and the strips
+    def scatter_field(self, full: torch.Tensor) -> torch.Tensor:
+        lv = self.LVL[0]
+        return full[lv.y0 * lv.L:(lv.y0 + lv.Ly) * lv.L].to(self.device, non_blocking=True).to(self.tdtype)
+
+    def gather_field(self, strip: torch.Tensor, host_full: torch.Tensor):
+        """Each rank writes its rows of the solution into its host buffer (the distributed end-to-end result)."""
+        lv = self.LVL[0]
+        host_full[lv.y0 * lv.L:(lv.y0 + lv.Ly) * lv.L].copy_(strip, non_blocking=True)
+
+
+def init(world: int, rank: int, local: int, backend: str = "nccl") -> Comm:
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, world_size=world, rank=rank, **kw)
+    return Comm(world, rank)
+
+
+def bcast_float(comm: Comm, v: float, src: int = 0) -> float:
+    dev = "cuda" if comm.backend == "nccl" else "cpu"
+    t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+    dist.broadcast(t, src, group=comm.group)
+    return float(t.item())
+
+
+def setup(U, params: MGParams, comm: Comm, init_fields: str = "device", null_vectors=None) -> DistMG:
+    """Distributed counterpart of the package-level setup(): U is the full link field (every rank keeps its rows)."""
+    from .mg import compute_near_null
+    mg = DistMG(params, comm)
+    if init_fields == "device":
+        mg.init_fields()
+    else:
+        raise ValueError("distributed setup draws its near-null seeds on the device (init_fields='device')")
+    mg.set_gauge(U)
+    gen_null = 1
+    if null_vectors is not None:
+        for lv, P in zip(mg.LVL, null_vectors):
+            P = torch.as_tensor(P).to(mg.tdtype)
+            if lv.distributed and P.shape[0] == lv.L * lv.L:
+                P = P[lv.y0 * lv.L:(lv.y0 + lv.Ly) * lv.L]
+            lv.phi_null = P.to(mg.device).contiguous().clone()
+        gen_null = 0
+    if params.nlevels > 0:
+        compute_near_null(mg, params.quad, gen_null)
+    elif params.matrix_free:
+        mg.LVL[0].D = None
+        mg.LVL[0].matrix_free = True
+    return mg

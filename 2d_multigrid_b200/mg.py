@@ -47,9 +47,12 @@ class Level:
     def __init__(self, mg: "MG", lvl: int):
         self.mg, self.lvl = mg, lvl
         p = mg.p
-        self.L = p.size[lvl]
+        self.L = p.size[lvl]       # global width (x); rows are strip-local
+        self.Ly = self.L           # locally owned rows [y0, y0+Ly)
+        self.y0 = 0
+        self.distributed = False   # True: 1-D strip in y with halo exchange; False: whole lattice on this GPU
         self.n = p.n_dof[lvl]
-        self.S = self.L * self.L
+        self.S = self.L * self.Ly  # local sites
         self.nc = p.n_dof[lvl + 1] if lvl < p.nlevels else None
         self.phi = None
         self.r = None
@@ -77,11 +80,25 @@ class Level:
             self._work[name] = torch.zeros(64 * 4, dtype=torch.float64, device=self.mg.device)
         return self._work[name]
 
-    def _halo(self, t: torch.Tensor):
-        """(lo, hi) row pointers for a field of this level: periodic wrap rows on one GPU."""
-        es = t.element_size() * self.n
-        base = t.data_ptr()
-        return base + (self.L - 1) * self.L * es, base
+    def set_strip(self, y0: int, Ly: int):
+        self.y0, self.Ly, self.distributed = y0, Ly, True
+        self.S = self.L * Ly
+
+    def _halo(self, t: torch.Tensor, nvec: int = 1, width: int | None = None):
+        """(lo, hi) row pointers for a field [S, width] (or a batch [nvec, S, width]) of this level: the periodic
+        wrap rows on one GPU, the exchanged neighbour rows (NCCL send/recv) on a strip."""
+        width = self.n if width is None else width
+        if self.distributed:
+            lo, hi = self.mg.comm.exchange_rows(t, self.L, self.Ly, width, nvec, key=(self.lvl, width, nvec))
+            return lo.data_ptr(), hi.data_ptr()
+        t0 = t if nvec == 1 else t[0]
+        es = t0.element_size() * width
+        base = t0.data_ptr()
+        return base + (self.Ly - 1) * self.L * es, base
+
+    def allreduce(self, t, op: str = "sum"):
+        if self.distributed:
+            self.mg.comm.allreduce(t, op)
 
     def init_level(self, gen: StdMT19937 | None):
         """f_init_level (S6/level.h:42-53): phi, r, phi_null drawn in this order (gen None -> ones, rand=0)."""
@@ -103,11 +120,16 @@ class Level:
         mg, p = self.mg, self.mg.p
         assert self.lvl == 0
         self.U = U
+        if self.distributed:   # link row below the strip: exchanged once
+            lo, _hi = mg.comm.exchange_rows(U, self.L, self.Ly, 2, 1, key=("U",))
+            self._U_lo = lo.clone()
+            self.U_lo_ptr = self._U_lo.data_ptr()
+        else:
+            self.U_lo_ptr = U.data_ptr() + (self.Ly - 1) * self.L * 2 * U.element_size()
         if store:
             self.D = torch.empty((self.S, 5, self.n, self.n), dtype=mg.tdtype, device=mg.device)
-            u_lo = U.data_ptr() + (self.L - 1) * self.L * 2 * U.element_size()
-            mg.ctx.call("mg2d_lvl0_matrix", _ptr(self.D), _ptr(U), u_lo, float(p.mass),
-                        0 if p.stencil == "wilson" else 1, self.L, self.L, mg.dcode, _stream())
+            mg.ctx.call("mg2d_lvl0_matrix", _ptr(self.D), _ptr(U), self.U_lo_ptr, float(p.mass),
+                        0 if p.stencil == "wilson" else 1, self.L, self.Ly, mg.dcode, _stream())
             self.D0inv = None
         self.matrix_free = not store
 
@@ -115,20 +137,21 @@ class Level:
         mg = self.mg
         if out.data_ptr() == vin.data_ptr():
             raise ValueError("stencil output must not alias its input")
-        lo, hi = self._halo(vin if nvec == 1 else vin[0])
         if self.matrix_free:
             if nvec != 1:
                 for v in range(nvec):
                     self._stencil(out[v], vin[v], None if b is None else b[v], mode,
                                   None if dots is None else dots[4 * v:], 1)
                 return
-            u_lo = self.U.data_ptr() + (self.L - 1) * self.L * 2 * self.U.element_size()
-            mg.ctx.call("mg2d_wilson_apply", _ptr(out), _ptr(vin), lo, hi, _ptr(self.U), u_lo, _ptr(b),
-                        float(mg.p.mass), self.L, self.L, mode, mg.dcode, _ptr(dots), _stream())
+            lo, hi = self._halo(vin)
+            mg.ctx.call("mg2d_wilson_apply", _ptr(out), _ptr(vin), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(b),
+                        float(mg.p.mass), self.L, self.Ly, mode, mg.dcode, _ptr(dots), _stream())
         else:
             vs = self.S * self.n
+            lo, hi = self._halo(vin, nvec)
+            hs = self.L * self.n if (self.distributed and nvec > 1) else vs
             mg.ctx.call("mg2d_stencil_apply", _ptr(out), _ptr(vin), lo, hi, _ptr(self.D), _ptr(b), self.n,
-                        self.L, self.L, mode, mg.dcode, nvec, vs, vs, _ptr(dots), _stream())
+                        self.L, self.Ly, mode, mg.dcode, nvec, vs, hs, _ptr(dots), _stream())
 
     def apply_D(self, v_out, v_in):
         """f_apply_D (S6/level.h:251-265): v_out = D v_in."""
@@ -143,7 +166,7 @@ class Level:
         ([0] = |r - D phi|^2, [3] = |r|^2).  No host sync."""
         d = self.dots("resmag")
         self._stencil(self.work("rtemp"), self.phi, self.r, _lib.MODE_RESID, d)
-        self.mg.allreduce(d[:4])
+        self.allreduce(d[:4])
         return d
 
     def get_residue_mag(self) -> float:
@@ -171,6 +194,8 @@ class Level:
         if num_iter <= 0:
             return
         if smoother == "gs":
+            if self.distributed:
+                raise MG2DError("lexicographic Gauss-Seidel is sequential across strips: use 'rbgs', 'jacobi' or 'mr' on multi-GPU levels")
             self._ensure_D0inv()
             mg.ctx.call("mg2d_relax_gs", _ptr(phi), _ptr(self.D), _ptr(self.D0inv), _ptr(r), self.n, self.L,
                         num_iter, mg.dcode, nvec, vs, _stream())
@@ -179,9 +204,10 @@ class Level:
             tmp = self.work("jacobi_tmp", None if nvec == 1 else nvec)
             cur, nxt = phi, tmp
             for _ in range(num_iter):
-                lo, hi = self._halo(cur if nvec == 1 else cur[0])
+                lo, hi = self._halo(cur, nvec)
+                hs = self.L * self.n if (self.distributed and nvec > 1) else vs
                 mg.ctx.call("mg2d_relax_jacobi", _ptr(nxt), _ptr(cur), lo, hi, _ptr(self.D), _ptr(self.D0inv),
-                            _ptr(r), self.n, self.L, self.L, mg.dcode, nvec, vs, vs, _stream())
+                            _ptr(r), self.n, self.L, self.Ly, mg.dcode, nvec, vs, hs, _stream())
                 cur, nxt = nxt, cur
             if cur.data_ptr() != phi.data_ptr():
                 mg.ctx.call("mg2d_copy", _ptr(phi), _ptr(cur), phi.numel(), mg.dcode, _stream())
@@ -192,26 +218,25 @@ class Level:
             self._stencil(res, phi, b, _lib.MODE_RESID, None, nvec)
             for _ in range(num_iter):
                 self._stencil(t, res, None, _lib.MODE_APPLY, d, nvec)
-                mg.allreduce(d[:4 * nvec])
+                self.allreduce(d[:4 * nvec])
                 mg.ctx.call("mg2d_mr_update", _ptr(phi), _ptr(res), _ptr(t), _ptr(d), float(mg.p.mr_omega),
                             vs, mg.dcode, nvec, vs, _stream())
         elif smoother == "rbgs":
-            hs = vs
+            hs = self.L * self.n if (self.distributed and nvec > 1) else vs
             for _ in range(num_iter):
                 for colour in (0, 1):
                     if self.matrix_free:
-                        u_lo = self.U.data_ptr() + (self.L - 1) * self.L * 2 * self.U.element_size()
                         for v in range(nvec):
                             ph = phi if nvec == 1 else phi[v]
                             rv = None if r is None else (r if nvec == 1 else r[v])
                             lo, hi = self._halo(ph)
-                            mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), u_lo, _ptr(rv),
-                                        float(mg.p.mass), self.L, self.L, colour, 0, mg.dcode, _stream())
+                            mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(rv),
+                                        float(mg.p.mass), self.L, self.Ly, colour, self.y0 & 1, mg.dcode, _stream())
                     else:
                         self._ensure_D0inv()
-                        lo, hi = self._halo(phi if nvec == 1 else phi[0])
+                        lo, hi = self._halo(phi, nvec)
                         mg.ctx.call("mg2d_relax_rb", _ptr(phi), lo, hi, _ptr(self.D), _ptr(self.D0inv), _ptr(r),
-                                    self.n, self.L, self.L, colour, 0, mg.dcode, nvec, vs, hs, _stream())
+                                    self.n, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, nvec, vs, hs, _stream())
         else:
             raise ValueError(smoother)
 
@@ -232,7 +257,7 @@ class Level:
             self.relax(p.null_chunk, phi=V, r=None)
             for v in range(nvec):
                 mg.ctx.call("mg2d_norm2", _ptr(V[v]), vs, mg.dcode, _ptr(nrm[v:]), _stream())
-            mg.allreduce(nrm[:nvec])
+            self.allreduce(nrm[:nvec])
             for v in range(nvec):
                 mg.ctx.call("mg2d_scale_inv_norm", _ptr(V[v]), _ptr(nrm[v:]), vs, mg.dcode, _stream())
         mg.ctx.call("mg2d_pack_null", _ptr(self.phi_null), _ptr(V), nvec, vs, nf, nc, self.S, int(wilson),
@@ -241,33 +266,63 @@ class Level:
     def norm_nn(self, quad: int):
         """f_norm_nn (S6/near_null.h:24-48)."""
         mg = self.mg
-        mg.ctx.call("mg2d_norm_nn", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad, mg.dcode, _stream())
+        mg.ctx.call("mg2d_norm_nn", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad, mg.dcode, _stream())
 
     def ortho(self, quad: int):
         """f_ortho (S6/near_null.h:97-173)."""
         mg = self.mg
-        mg.ctx.call("mg2d_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad, mg.dcode,
+        mg.ctx.call("mg2d_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad, mg.dcode,
                     _ptr(mg.status), _stream())
 
     def check_ortho(self, quad: int) -> float:
         """f_check_ortho (S6/near_null.h:175-214): worst |<null_d1, null_d2>| over aggregates."""
         mg = self.mg
         out = self.dots("ortho_check")
-        mg.ctx.call("mg2d_check_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.L, mg.p.block, quad,
+        mg.ctx.call("mg2d_check_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad,
                     mg.dcode, _ptr(out), _stream())
+        self.allreduce(out[:1], "max")
         return float(out[0].item())
 
     def restriction(self, vec_c, vec_f, quad: int):
         """f_restriction (S6/near_null.h:217-240): vec_c = P vec_f."""
         mg = self.mg
-        mg.ctx.call("mg2d_restrict", _ptr(vec_c), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.L,
+        gather = self.distributed and not self._coarse_distributed()
+        if self.distributed and quad != 1:
+            raise MG2DError("shifted aggregates (quad != 1) need the whole lattice on one GPU")
+        dst = vec_c
+        if gather:   # the coarse level is replicated: restrict the local strip, then all-gather the strips
+            dst = self.work_coarse_strip()
+        mg.ctx.call("mg2d_restrict", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
                     mg.p.block, quad, mg.dcode, _stream())
+        if gather:
+            mg.comm.allgather(vec_c, dst)
 
     def prolongation(self, vec_f, vec_c, quad: int, zero_vc: bool = False):
         """f_prolongation (S6/near_null.h:242-264): vec_f += P^dagger vec_c.  `self` is the FINE level."""
         mg = self.mg
-        mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(vec_c), _ptr(self.phi_null), self.n, self.nc, self.L, self.L,
+        if self.distributed and not self._coarse_distributed():
+            # replicated coarse level: every rank prolongs from its rows of the full coarse field
+            blk = mg.p.block
+            Lc = self.L // blk
+            view = vec_c[(self.y0 // blk) * Lc:(self.y0 // blk + self.Ly // blk) * Lc]
+            mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(view), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
+                        blk, quad, 0, mg.dcode, _stream())
+            if zero_vc:
+                mg.ctx.call("mg2d_zero", _ptr(vec_c), vec_c.numel(), mg.dcode, _stream())
+            return
+        mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(vec_c), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
                     mg.p.block, quad, int(zero_vc), mg.dcode, _stream())
+
+    def _coarse_distributed(self) -> bool:
+        nxt = self.mg.LVL[self.lvl + 1] if self.lvl + 1 < len(self.mg.LVL) else None
+        return bool(nxt is not None and nxt.distributed)
+
+    def work_coarse_strip(self):
+        blk = self.mg.p.block
+        key = ("coarse_strip", None)
+        if key not in self._work:
+            self._work[key] = torch.zeros(((self.Ly // blk) * (self.L // blk), self.nc), dtype=self.mg.tdtype, device=self.mg.device)
+        return self._work[key]
 
 
 # ==========================================================================================================
@@ -286,6 +341,7 @@ class MG:
         self.LVL = [Level(self, l) for l in range(params.nlevels + 1)]
         self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
         self.info = {}
+        self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
         self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
 
     @property
@@ -297,8 +353,9 @@ class MG:
     def to_device(self, a) -> torch.Tensor:
         return torch.as_tensor(np.ascontiguousarray(a)).to(self.tdtype).to(self.device)
 
-    def allreduce(self, t):   # single GPU: nothing to do (multi-GPU strips override this)
-        return
+    def allreduce(self, t, op: str = "sum"):
+        """Global reduction of level-0 partial sums (no-op on one GPU)."""
+        self.LVL[0].allreduce(t, op)
 
     # ---- main() steps ------------------------------------------------------------------------------------
     def init_reference_fields(self):
@@ -312,17 +369,25 @@ class MG:
     def init_fields(self, generator_seed: int | None = None):
         """Device-side initialisation for lattices too large for the host RNG stream: phi = 0, r = 0,
         phi_null ~ U(-pi, pi) from torch's generator."""
-        g = torch.Generator(device=self.device)
-        g.manual_seed(self.p.seed if generator_seed is None else generator_seed)
+        seed = self.p.seed if generator_seed is None else generator_seed
+        rank = 0 if self.comm is None else self.comm.rank
         for lv in self.LVL:
+            g = torch.Generator(device=self.device)
+            # strips draw rank-specific seeds; replicated levels must be identical on every rank
+            g.manual_seed(seed + 7919 * lv.lvl + (104729 * (rank + 1) if lv.distributed else 0))
             lv.phi, lv.r = lv.new_field(), lv.new_field()
             if lv.lvl != self.p.nlevels:
                 re = (torch.rand((lv.S, lv.nc, lv.n), generator=g, dtype=torch.float64, device=self.device) * 2 - 1) * math.pi
                 lv.phi_null = re.to(self.tdtype)
 
     def set_gauge(self, U):
-        U = torch.as_tensor(U).to(self.tdtype).to(self.device).contiguous()
-        self.LVL[0].compute_lvl0_matrix(U, store=True)
+        """U: the full link field [L*L, 2] (each strip keeps its own rows) or already the local rows."""
+        lv0 = self.LVL[0]
+        U = torch.as_tensor(U)
+        if lv0.distributed and U.shape[0] == lv0.L * lv0.L:
+            U = U[lv0.y0 * lv0.L:(lv0.y0 + lv0.Ly) * lv0.L]
+        U = U.to(self.tdtype).to(self.device).contiguous()
+        lv0.compute_lvl0_matrix(U, store=True)
 
 
 # ---- modules_main.h --------------------------------------------------------------------------------------
@@ -353,9 +418,16 @@ def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
     lvl_c.D = torch.empty((lvl_c.S, 5, nc, nc), dtype=mg.tdtype, device=mg.device)
     lvl_c.D0inv = None
     P = lvl_P.phi_null
-    es = P.element_size() * nc * nf
-    p_lo, p_hi = P.data_ptr() + (lvl_f.L - 1) * lvl_f.L * es, P.data_ptr()
-    mg.ctx.call("mg2d_coarse_matrix", _ptr(lvl_c.D), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.L,
+    p_lo, p_hi = lvl_f._halo(P, 1, nc * nf)          # projector rows below / above the strip (or the periodic wrap)
+    if lvl_f.distributed and not lvl_c.distributed:
+        # first replicated level: every rank builds its strip of D_c, then the strips are all-gathered
+        blk = mg.p.block
+        strip = torch.empty(((lvl_f.Ly // blk) * (lvl_f.L // blk), 5, nc, nc), dtype=mg.tdtype, device=mg.device)
+        mg.ctx.call("mg2d_coarse_matrix", _ptr(strip), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.Ly,
+                    blk, quad, mg.dcode, _stream())
+        mg.comm.allgather(lvl_c.D, strip)
+        return
+    mg.ctx.call("mg2d_coarse_matrix", _ptr(lvl_c.D), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.Ly,
                 mg.p.block, quad, mg.dcode, _stream())
 
 
@@ -383,6 +455,8 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
             nt.ortho(q + 1)
             worst.append(nt.check_ortho(q + 1))
             compute_coarse_matrix(mg.NTL[p.nlevels][q], mg.LVL[lo], nt, q + 1)
+    if mg.comm is not None:
+        mg.comm.allreduce(mg.status, "max")
     st = mg.status.cpu()
     if int(st[0]) != 0:
         raise FloatingPointError(f"near-null orthonormalisation failed (status {int(st[0])}): NaN or tiny norm "
@@ -437,7 +511,7 @@ def min_res(mg: MG, num_copies: int, level: int) -> torch.Tensor:
         mg.ctx.call("mg2d_cdot_batch", _ptr(E), vs, num_copies, _ptr(lv.r), vs, 1, vs, mg.dcode, _ptr(src), _stream())
     else:                        # src_i = <r, D e_i> (:358-366)
         mg.ctx.call("mg2d_cdot_batch", _ptr(lv.r), vs, 1, _ptr(T), vs, num_copies, vs, mg.dcode, _ptr(src), _stream())
-    mg.allreduce(buf[0:40])
+    lv.allreduce(buf[0:40])
     mg.ctx.call("mg2d_minres_solve", _ptr(gram), _ptr(src), num_copies, _ptr(a), _stream())
     return a
 

@@ -281,6 +281,7 @@ def main():
     nbytes = L * L * 2 * 16
 
     if rank != 0:
+        _finish(comm)
         return
 
     # ---- per-kernel rooflines (rank 0, local data; inputs >> L2 or L2 flushed) -----------------------------
@@ -350,7 +351,20 @@ def main():
         "kernels": table,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    _finish(comm)
+
+
+def _finish(comm):
+    """Leave without tearing NCCL down under live CUDA graphs that captured its kernels (that hangs): all ranks
+    synchronise, flush and exit."""
+    if comm is None:
+        return
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
