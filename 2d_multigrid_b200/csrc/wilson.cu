@@ -54,7 +54,7 @@ __device__ __forceinline__ void store_spinor(cplx<T>* __restrict__ p, size_t s, 
 }
 
 constexpr int WX = 128;       // threads per CTA = x-extent of a CTA column strip
-constexpr int RY = 32;        // rows marched per work item
+constexpr int RY_MAX = 32;    // rows marched per work item (fewer on small lattices, to keep every SM busy)
 
 // MODE 0: out = D in ; MODE 1: out = b - D in.  DOTS: also reduce |out|^2, <out,in>, |b|^2.
 template <typename T, int MODE, bool DOTS>
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(WX)
 wilson_march_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in,
                     const cplx<T>* __restrict__ in_lo, const cplx<T>* __restrict__ in_hi,
                     const cplx<T>* __restrict__ U, const cplx<T>* __restrict__ U_lo,
-                    const cplx<T>* __restrict__ b, T diag, int Lx, int Ly,
+                    const cplx<T>* __restrict__ b, T diag, int Lx, int Ly, int RY,
                     double* __restrict__ partials, unsigned int* __restrict__ counter,
                     double* __restrict__ dots) {
     using C = cplx<T>;
@@ -225,14 +225,15 @@ int launch_wilson(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, c
                   const void* U_lo, const void* b, double mass, int Lx, int Ly, int mode, double* dots,
                   cudaStream_t st) {
     using C = cplx<T>;
+    // rows per work item: as many as possible (each item re-reads 2 halo rows) while >= 6 CTAs per SM exist
+    int RY = RY_MAX;
+    while (RY > 4 && ((Lx + WX - 1) / WX) * ((Ly + RY - 1) / RY) < ctx->num_sms * 6) RY >>= 1;
     const int nwork = ((Lx + WX - 1) / WX) * ((Ly + RY - 1) / RY);
     int grid = nwork < MG2D_MAX_PARTIALS ? nwork : MG2D_MAX_PARTIALS;
-    const int cap = ctx->num_sms * 16;
-    if (grid > cap) grid = cap;
     const T diag = (T)(2.0 + mass);
 #define WL(MODE, DOTS)                                                                                      \
     wilson_march_kernel<T, MODE, DOTS><<<grid, WX, 0, st>>>((C*)out, (const C*)in, (const C*)in_lo,          \
-        (const C*)in_hi, (const C*)U, (const C*)U_lo, (const C*)b, diag, Lx, Ly, ctx->partials, ctx->counter, dots)
+        (const C*)in_hi, (const C*)U, (const C*)U_lo, (const C*)b, diag, Lx, Ly, RY, ctx->partials, ctx->counter, dots)
     if (mode == MG2D_MODE_APPLY) { if (dots) WL(0, true); else WL(0, false); }
     else                         { if (dots) WL(1, true); else WL(1, false); }
 #undef WL

@@ -95,6 +95,7 @@ class DistMG(MG):
     def __init__(self, params: MGParams, comm: Comm, device: int | None = None, min_rows: int = MIN_ROWS):
         super().__init__(params, device)
         self.comm = comm
+        self.min_rows = min_rows
         if params.ntl:
             raise NotImplementedError("the non-telescoping cycle shifts aggregates across strip boundaries: one GPU only")
         self.plan = plan_strips(params, comm.world, min_rows)

@@ -342,6 +342,7 @@ class MG:
         self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
         self.info = {}
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
+        self.min_rows = 0
         self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
 
     @property
@@ -388,6 +389,37 @@ class MG:
             U = U[lv0.y0 * lv0.L:(lv0.y0 + lv0.Ly) * lv0.L]
         U = U.to(self.tdtype).to(self.device).contiguous()
         lv0.compute_lvl0_matrix(U, store=True)
+
+
+def make_single_precision(mg: "MG") -> "MG":
+    """complex64 shadow of a set-up hierarchy (links, stored operators, projectors), used as the preconditioner
+    of the fp64 outer GCR: every V-cycle kernel then moves half the bytes.  The outer residual, the GCR vectors
+    and the convergence test stay in complex128, so the 1e-10 TRUE residual is unaffected."""
+    import dataclasses
+    if mg.p.dtype != "complex128":
+        raise ValueError("make_single_precision expects a complex128 hierarchy")
+    p32 = dataclasses.replace(mg.p, dtype="complex64", size=[], n_dof=[])
+    if mg.comm is not None:
+        from .dist import DistMG
+        m32 = DistMG(p32, mg.comm, min_rows=mg.min_rows)
+    else:
+        m32 = MG(p32, mg.device_index)
+    c64 = torch.complex64
+    for lv, l32 in zip(mg.LVL, m32.LVL):
+        l32.phi, l32.r = l32.new_field(), l32.new_field()
+        if lv.phi_null is not None:
+            l32.phi_null = lv.phi_null.to(c64)
+        if lv.D is not None:
+            l32.D = lv.D.to(c64)
+        l32.matrix_free = lv.matrix_free
+        if lv.U is not None:
+            l32.U = lv.U.to(c64)
+            if lv.distributed:
+                l32._U_lo = lv._U_lo.to(c64)
+                l32.U_lo_ptr = l32._U_lo.data_ptr()
+            else:
+                l32.U_lo_ptr = l32.U.data_ptr() + (l32.Ly - 1) * l32.L * 2 * l32.U.element_size()
+    return m32
 
 
 # ---- modules_main.h --------------------------------------------------------------------------------------
@@ -680,7 +712,7 @@ def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, c
 
 
 def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, restart: int = 8, check_every: int = 1,
-           use_graph: bool = False):
+           use_graph: bool = False, precond: "MG | None" = None):
     """Flexible GCR(restart) around one multigrid cycle as preconditioner (mirrors oracle gcr_MG; the reference
     itself only iterates the cycle stationarily).  On entry LVL[0].phi / LVL[0].r hold x0 / b; on exit the
     solution is in LVL[0].phi.  All scalars (Gram-Schmidt coefficients, step lengths) stay on the device."""
@@ -699,13 +731,15 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
     lv0._stencil(r, x, b, _lib.MODE_RESID, None)
     call("mg2d_norm2", _ptr(b), vs, dc, _ptr(sc[5:]), st())
     mg.allreduce(sc[5:6])
-    for lv in mg.LVL[1:]:
-        call("mg2d_zero", _ptr(lv.phi), lv.S * lv.n, dc, st())
+    pm = mg if precond is None else precond      # hierarchy that runs the cycle (may be the complex64 shadow)
+    pl0 = pm.LVL[0]
+    for lv in pm.LVL[1:]:
+        pm.ctx.call("mg2d_zero", _ptr(lv.phi), lv.S * lv.n, pm.dcode, st())
     cyc = None
     if use_graph:
-        cyc = mg.info.get("precond_graph")
+        cyc = pm.info.get("precond_graph")
         if cyc is None:
-            cyc = mg.info["precond_graph"] = CycleGraph(mg, with_resmag=False)
+            cyc = pm.info["precond_graph"] = CycleGraph(pm, with_resmag=False)
     ntl = p.ntl and p.nlevels > 0
     info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
     hist = torch.zeros(max(check_every, 1), dtype=torch.float64, device=mg.device)
@@ -716,16 +750,16 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         nb = min(check_every, max_iters - it)
         for k in range(nb):
             # z = M(r): the cycle works on (LVL[0].phi, LVL[0].r)
-            call("mg2d_zero", _ptr(lv0.phi), vs, dc, st())
-            call("mg2d_copy", _ptr(lv0.r), _ptr(r), vs, dc, st())
+            pm.ctx.call("mg2d_zero", _ptr(pl0.phi), vs, pm.dcode, st())
+            pm.ctx.call("mg2d_convert", _ptr(pl0.r), pm.dcode, _ptr(r), dc, vs, st())
             if cyc is not None:
                 cyc.run()
             elif ntl:
-                MG_ntl(mg)
+                MG_ntl(pm)
             else:
-                MG_simple(mg)
+                MG_simple(pm)
             z, w = Z[slot], W[slot]
-            call("mg2d_copy", _ptr(z), _ptr(lv0.phi), vs, dc, st())
+            pm.ctx.call("mg2d_convert", _ptr(z), dc, _ptr(pl0.phi), pm.dcode, vs, st())
             lv0._stencil(w, z, None, _lib.MODE_APPLY, None)
             for j in range(slot):
                 call("mg2d_cdot_batch", _ptr(W[j]), vs, 1, _ptr(w), vs, 1, vs, dc, _ptr(sc), st())

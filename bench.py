@@ -257,6 +257,23 @@ def main():
         torch.cuda.profiler.stop()
         del tmp_a, tmp_b
 
+    # ---- the same solve with the V-cycle preconditioner in complex64 (outer GCR / residual stay complex128) ----
+    def mixed_solve():
+        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4, precond_dtype="complex64")
+    for _ in range(3):
+        xm, info_m = mixed_solve()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xm, info_m = mixed_solve()
+    e1.record()
+    barrier()
+    ms_mixed = e0.elapsed_time(e1) / args.steps
+    if comm is not None:
+        t = torch.tensor([ms_mixed], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_mixed = float(t.item())
+
     # ---- end to end: host rhs -> H2D -> solve -> D2H solution -----------------------------------------------
     def e2e_solve():
         r = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev, non_blocking=True)
@@ -313,11 +330,14 @@ def main():
     # share of one V-cycle (nu = 4 pre + 4 post sweeps per level) taken by the level-1 smoother, from these timings
     dom = max(table[1:3], key=lambda r: r["ms"]) if len(table) > 2 else table[0]
     dapply = table[0]
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    # dram bytes per launch from the committed ncu capture (profiles/traffic_L1024.json) apply to the L=1024 workload
     traffic = None
+    traffic_file = os.path.join(ROOT, "profiles", f"traffic_L{L}.json")
     if os.path.exists(traffic_file):
         try:
             traffic = json.load(open(traffic_file)).get(dom["kernel"].split(" ")[0])
+            if traffic is not None and " x2 " in dom["kernel"]:
+                traffic *= 2          # the timed unit is a full sweep = two half-sweep launches
         except Exception:
             traffic = None
 
@@ -348,6 +368,8 @@ def main():
                      "frac": dom["frac"], "traffic": traffic, "peak_source": pk_src},
         "dapply": {"kernel": dapply["kernel"], "bound": "hbm", "achieved": dapply["gbs"], "peak": hbm, "unit": "GB/s",
                    "frac": dapply["frac"], "bytes_per_site": 96, "us": dapply["ms"] * 1e3, "target_frac": 0.70},
+        "mixed_precision": {"value": ms_mixed, "unit": UNIT, "iters": info_m["iters"], "final_true_residual": info_m.get("true_resnorm"),
+                            "note": "same solve, V-cycle preconditioner on a complex64 copy of the hierarchy; outer FGCR, residual and the 1e-10 test in complex128"},
         "kernels": table,
         "cpu_baseline": cpu,
     }
