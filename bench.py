@@ -206,6 +206,10 @@ def main():
     L = args.L
     pk, pk_src = peaks()
 
+    def log(msg):
+        if rank == 0:
+            print(f"# [{time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
     # ---- inputs (not timed): links, critical mass, hierarchy ---------------------------------------------
     t0 = time.time()
     th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=60, seed=1234, device=str(dev))
@@ -246,9 +250,11 @@ def main():
         return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4)
 
     # ---- device-resident steps ------------------------------------------------------------------------
+    log("warm-up solves")
     for _ in range(max(args.warmup, 3)):
         x, info = one_solve()
     barrier()
+    log(f"timed solves (iters {info['iters']}, true residual {info.get('true_resnorm')})")
     n0 = mg.launches
     sampler = ClockSampler(local)
     sampler.start()
@@ -267,6 +273,7 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
 
+    log(f"mixed {ms_mixed:.1f} ms; e2e leg")
     if args.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -277,6 +284,7 @@ def main():
         torch.cuda.profiler.stop()
         del tmp_a, tmp_b
 
+    log(f"c128 {ms:.1f} ms; mixed-precision leg")
     # ---- the same solve with the V-cycle preconditioner in complex64 (outer GCR / residual stay complex128) ----
     def mixed_solve():
         return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4, precond_dtype="complex64")
@@ -317,17 +325,14 @@ def main():
         e2e_ms = float(t.item())
     nbytes = L * L * 2 * 16
 
-    if rank != 0:
-        _finish(comm)
-        return
-
-    # ---- per-kernel rooflines (rank 0, local data; inputs >> L2 or L2 flushed) -----------------------------
+    log("e2e done; kernel timings")
+    # ---- per-kernel rooflines (every rank runs them: strip-level kernels exchange halos; rank 0 reports) -------
     flush = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # 256 MiB > 126 MB L2
     hbm = float(pk["hbm_gbs"])
     kern = []
     a, b_ = lv0.new_field(), lv0.new_field()
     a.normal_()
-    S0 = lv0.S
+    S0 = lv0.S            # local sites (strip)
     t_apply = time_kernel(lambda: lv0.apply_D(b_, a), 20, flush)
     kern.append(("wilson_march_kernel<double> (D-apply, matrix-free)", 96.0 * S0, t_apply))
     lv0.phi.copy_(a)
@@ -346,6 +351,10 @@ def main():
         kern.append((f"restrict_kernel<double,2,{n1}> (level 0->1)", ((n1 * 2 + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
         t_pro = time_kernel(lambda: lv0.prolongation(b_, l1.phi, 1), 10, flush)
         kern.append((f"prolong_kernel<double,2,{n1}> (level 1->0)", ((n1 * 2 + 2 * 2) * 16.0 + n1 * 16.0 / 16) * S0, t_pro))
+    barrier()
+    if rank != 0:
+        _finish(comm)
+        return
     table = [{"kernel": k, "bytes": by, "ms": t, "gbs": by / t / 1e6, "frac": by / t / 1e6 / hbm} for k, by, t in kern]
     # share of one V-cycle (nu = 4 pre + 4 post sweeps per level) taken by the level-1 smoother, from these timings
     dom = max(table[1:3], key=lambda r: r["ms"]) if len(table) > 2 else table[0]
