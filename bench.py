@@ -103,10 +103,14 @@ def workload_params(mg2d, L, mass, **kw):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def oracle_sample(L_cpu: int, iters_cap: int, seed_delta: float = 1e-3):
-    """The numpy oracle on a bounded sample of the workload: same hierarchy shape (block 4, 16 coarse dof,
-    rbgs 4+4, GCR(8)), lattice L_cpu, at most iters_cap outer iterations.  Returns seconds per (site*iteration),
-    setup seconds per site, iterations done."""
+CPU_SAMPLE_L = 256        # lattice of the bounded CPU sample (same hierarchy shape as the workload)
+CPU_SAMPLE_ITERS = 6      # outer iterations timed per sample (~7 s of numpy work)
+
+
+def oracle_setup(L_cpu: int):
+    """Hierarchy of the numpy oracle on a bounded sample of the workload: same shape (block 4, 16 coarse dof,
+    rbgs 4+4, GCR(8)), lattice L_cpu.  Not timed."""
+    import copy
     import numpy as np
     from oracle import mg_oracle as O
     nlevels = max(1, int(round(math.log(L_cpu / 16, 4))))
@@ -114,16 +118,20 @@ def oracle_sample(L_cpu: int, iters_cap: int, seed_delta: float = 1e-3):
     U = O.gauge_from_phases(th)
     po = O.Params(L=L_cpu, num_iters=4, block=4, m=-0.05, nlevels=nlevels, stencil="wilson", smoother="rbgs",
                   n_dof_scale=16, null_iters=20)
-    t0 = time.perf_counter()
     LVL, NTL = O.build_reference_problem(po, U)
     O.compute_near_null(LVL, NTL, po, 1)
-    t_setup = time.perf_counter() - t0
     b = np.zeros((L_cpu * L_cpu, 2), dtype=complex)
     b[L_cpu // 2 + (L_cpu // 2) * L_cpu, 0] = 1.0
+    return {"O": O, "po": po, "LVL": LVL, "NTL": NTL, "b": b, "L": L_cpu, "copy": copy}
+
+
+def oracle_solve(st, iters_cap: int):
+    """Time `iters_cap` outer iterations of the oracle's GCR+V-cycle; returns (seconds per site*iteration, iterations, seconds)."""
+    LVL = st["copy"].deepcopy(st["LVL"])
     t0 = time.perf_counter()
-    _, info = O.gcr_MG(LVL, NTL, po, b, tol=TOL, max_iters=iters_cap, restart=8)
-    t_solve = time.perf_counter() - t0
-    return t_solve / (info["iters"] * L_cpu * L_cpu), t_setup / (L_cpu * L_cpu), info["iters"], t_solve
+    _, info = st["O"].gcr_MG(LVL, st["NTL"], st["po"], st["b"], tol=TOL, max_iters=iters_cap, restart=8)
+    dt = time.perf_counter() - t0
+    return dt / (info["iters"] * st["L"] ** 2), info["iters"], dt
 
 
 def run_reference_arm(args):
@@ -132,24 +140,23 @@ def run_reference_arm(args):
     if rank != 0:
         return
     L = args.L
-    Lc = 128
-    import numpy as np  # noqa: F401
     cores = os.cpu_count() or 1
     iters_gpu = args.ref_iters
-    vals = []
+    st = oracle_setup(CPU_SAMPLE_L)
     for _ in range(args.warmup):
-        oracle_sample(Lc, 2)
+        oracle_solve(st, 2)
+    vals = []
     for _ in range(args.steps):
-        per_site_iter, _, it_done, t = oracle_sample(Lc, 3)
+        per_site_iter, it_done, dt = oracle_solve(st, CPU_SAMPLE_ITERS)
         vals.append(per_site_iter * L * L * iters_gpu * 1e3)
     v = sum(vals) / len(vals)
-    sample = (f"numpy oracle port, {Lc}^2 lattice with the workload's hierarchy shape (block 4, 16 coarse dof, rbgs 4+4, "
-              f"GCR(8)), 3 outer iterations timed; scaled per site and per iteration to {L}^2 x {iters_gpu} iterations "
-              f"(extrapolated; numpy/BLAS may use up to {cores} threads)")
+    sample = (f"numpy oracle port, {CPU_SAMPLE_L}^2 lattice with the workload's hierarchy shape (block 4, 16 coarse dof, rbgs 4+4, "
+              f"GCR(8)), {CPU_SAMPLE_ITERS} outer iterations timed per step; scaled per site and per iteration to {L}^2 x {iters_gpu} "
+              f"iterations (extrapolated; numpy may use up to {cores} threads)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "tol": TOL},
+            "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "tol": TOL, "iters": iters_gpu},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -181,7 +188,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=4096)
     ap.add_argument("--delta", type=float, default=1e-3, help="mass offset above the estimated critical mass")
-    ap.add_argument("--ref-iters", type=int, default=20, help="outer iterations assumed by the reference arm's scaling")
+    ap.add_argument("--ref-iters", type=int, default=14,
+                    help="outer iterations of the workload solve (14 measured by the GPU arm at 4096^2) used to scale the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra solve (+ one D-apply) with cudaProfilerStart/Stop for `ncu --profile-from-start off`; "
@@ -273,7 +281,6 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
 
-    log(f"mixed {ms_mixed:.1f} ms; e2e leg")
     if args.profile_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -302,6 +309,7 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_mixed = float(t.item())
 
+    log(f"mixed {ms_mixed:.1f} ms; e2e leg")
     # ---- end to end: host rhs -> H2D -> solve -> D2H solution -----------------------------------------------
     def e2e_solve():
         r = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev, non_blocking=True)
@@ -373,8 +381,8 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): bounded oracle sample, scaled ----------------------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        Lc = 128
-        per_site_iter, setup_per_site, it_done, t_cpu = oracle_sample(Lc, 3)
+        Lc = CPU_SAMPLE_L
+        per_site_iter, it_done, t_cpu = oracle_solve(oracle_setup(Lc), CPU_SAMPLE_ITERS)
         cpu = {"value": per_site_iter * L * L * info["iters"] * 1e3, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": (f"numpy oracle port, same algorithm on a {Lc}^2 lattice (block 4, 16 coarse dof, rbgs 4+4, GCR(8)), "
                           f"{it_done} outer iterations in {t_cpu:.1f}s; scaled per site x iteration to {L}^2 x {info['iters']} "
