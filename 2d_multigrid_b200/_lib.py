@@ -45,6 +45,9 @@ SIGNATURES = {
     "mg2d_coarse_matrix": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mg2d_minres_solve": [_vp, _vp, _i, _vp, _vp],
     "mg2d_scale_phi": [_vp, _vp, _ll, _vp, _i, _ll, _i, _vp],
+    "mg2d_ipc_alloc": [_ll, C.POINTER(_vp), _vp],
+    "mg2d_ipc_open": [_vp, C.POINTER(_vp)],
+    "mg2d_halo_exchange": [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "mg2d_s2_relax": [_vp, _vp, _i, _d, _d, _i, _i, _vp],
     "mg2d_s2_project": [_vp, _vp, _vp, _i, _d, _d, _i, _vp],
     "mg2d_s2_interpolate": [_vp, _vp, _i, _i, _vp],

@@ -373,3 +373,110 @@ extern "C" int mg2d_axpy_ratio2(mg2d_ctx* ctx, void* y, const void* x, void* y2,
         (axpy_ratio2_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)y, (const float2*)x, (float2*)y2, (const float2*)x2, num, den, sign, nelem)),
         "mg2d_axpy_ratio2");
 }
+
+// =========================================================================================================
+// Peer-to-peer halo exchange over NVLink (multi-GPU strips): ONE kernel per exchange that (1) tells both
+// neighbours their previous rows were consumed, (2) waits for the neighbours' acknowledgements, (3) stores
+// this rank's boundary rows straight into the neighbours' halo buffers (mapped peer memory, CUDA IPC),
+// (4) publishes the new epoch with a system-scope release and (5) waits for both neighbours' rows.
+// No NCCL call, no host involvement; the epoch counter lives in device memory so the kernel can be replayed
+// from a CUDA graph.  A bounded spin turns a lost peer into an error flag instead of a hang.
+// =========================================================================================================
+namespace {
+
+struct HaloSlot {            // one per (level, width, nvec, dtype); identical offsets on every rank
+    unsigned long long flag_lo, flag_hi;     // written by prev / next: epoch of the rows now in lo_buf / hi_buf
+    unsigned long long ack_prev, ack_next;   // written by prev / next: last epoch of MY rows they have consumed
+    unsigned long long epoch;                // local
+    unsigned long long error;
+    unsigned long long pad[2];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
+    for (long long it = 0; it < (1ll << 24); ++it) {
+        if (ld_acquire_sys(p) >= want) return true;
+        __nanosleep(200);
+    }
+    return false;
+}
+
+// first/last: this rank's boundary rows (nvec pieces of row_bytes, `src_stride` bytes apart);
+// peer_lo_of_next / peer_hi_of_prev: the neighbours' halo buffers; slots: mine and the two neighbours'.
+__global__ void __launch_bounds__(1024)
+halo_exchange_kernel(const uint4* __restrict__ first, const uint4* __restrict__ last, long long src_stride16,
+                     long long row16, int nvec, uint4* __restrict__ next_lo, uint4* __restrict__ prev_hi,
+                     HaloSlot* mine, HaloSlot* prev, HaloSlot* next) {
+    __shared__ unsigned long long s_epoch;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long e = mine->epoch;
+        s_epoch = e;
+        st_release_sys(&prev->ack_next, e);      // I am prev's "next": its rows of epoch e (my lo_buf) are consumed
+        st_release_sys(&next->ack_prev, e);
+        s_ok = spin_until(&mine->ack_next, e) && spin_until(&mine->ack_prev, e);
+    }
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    if (s_ok) {
+        for (int v = 0; v < nvec; ++v)
+            for (long long k = threadIdx.x; k < row16; k += blockDim.x) {
+                next_lo[(size_t)v * row16 + k] = last[(size_t)v * src_stride16 + k];
+                prev_hi[(size_t)v * row16 + k] = first[(size_t)v * src_stride16 + k];
+            }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st_release_sys(&next->flag_lo, e + 1);
+        st_release_sys(&prev->flag_hi, e + 1);
+        const bool ok = s_ok && spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
+        if (!ok) mine->error = 1;
+        mine->epoch = e + 1;
+    }
+}
+
+}  // namespace
+
+extern "C" int mg2d_ipc_alloc(mg2d_ctx* ctx, long long bytes, void** ptr, void* handle64) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!ptr || !handle64 || bytes < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_ipc_alloc: bad argument");
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc(ptr, (size_t)bytes) != cudaSuccess || cudaMemset(*ptr, 0, (size_t)bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&h, *ptr) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "mg2d_ipc_alloc: %s", cudaGetErrorString(cudaGetLastError()));
+        return MG2D_ECUDA;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(handle64, &h, 64);
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_ipc_open(mg2d_ctx* ctx, const void* handle64, void** ptr) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!ptr || !handle64) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "mg2d_ipc_open: %s", cudaGetErrorString(e)); cudaGetLastError(); return MG2D_ECUDA; }
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_halo_exchange(mg2d_ctx* ctx, const void* first, const void* last, long long src_stride_bytes,
+                                  long long row_bytes, int nvec, void* next_lo, void* prev_hi, void* slot_mine,
+                                  void* slot_prev, void* slot_next, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!first || !last || !next_lo || !prev_hi || !slot_mine || !slot_prev || !slot_next || nvec < 1 || row_bytes < 16 ||
+        (row_bytes & 15) || (src_stride_bytes & 15))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_halo_exchange: bad argument (rows must be multiples of 16 bytes)");
+    halo_exchange_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const uint4*)first, (const uint4*)last, src_stride_bytes / 16,
+        row_bytes / 16, nvec, (uint4*)next_lo, (uint4*)prev_hi, (HaloSlot*)slot_mine, (HaloSlot*)slot_prev, (HaloSlot*)slot_next);
+    return mg2d_check_launch(ctx, "mg2d_halo_exchange");
+}

@@ -21,6 +21,7 @@ host logic without GPUs.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -30,6 +31,19 @@ from .mg import MG
 from .params import MGParams
 
 MIN_ROWS = int(os.environ.get("MG2D_MIN_ROWS", "32"))
+HALO_MODE = os.environ.get("MG2D_HALO", "p2p")      # 'p2p': one fused NVLink kernel per exchange; 'nccl': send/recv
+SLAB_BYTES = int(os.environ.get("MG2D_P2P_SLAB_MB", "192")) << 20
+SLOT_REGION = 1 << 16                                # 1024 slots of 64 bytes at the start of the slab
+
+
+class _Ptr:
+    """Minimal stand-in for a tensor where only the address is needed."""
+
+    def __init__(self, ptr: int):
+        self._p = ptr
+
+    def data_ptr(self) -> int:
+        return self._p
 
 
 def plan_strips(p: MGParams, world: int, min_rows: int = MIN_ROWS):
@@ -50,10 +64,66 @@ class Comm:
         self.prev, self.next = (rank - 1) % world, (rank + 1) % world
         self._halo = {}
         self.backend = dist.get_backend(group)
+        self.p2p = None            # set by enable_p2p()
 
-    def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None):
+    # ---- peer-to-peer path: CUDA-IPC slab + one fused exchange kernel (mg2d_halo_exchange) --------------------
+    def enable_p2p(self, ctx, device, slab_bytes: int = SLAB_BYTES):
+        """Allocate this rank's slab, trade IPC handles, map the two neighbours' slabs."""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        ctx.call("mg2d_ipc_alloc", slab_bytes, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        base = {self.rank: ptr.value}
+        for peer in {self.prev, self.next} - {self.rank}:
+            hb = (ctypes.c_ubyte * 64)(*allh[peer].cpu().tolist())
+            pp = ctypes.c_void_p()
+            ctx.call("mg2d_ipc_open", ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(pp))
+            base[peer] = pp.value
+        dist.barrier(group=self.group)
+        self.p2p = {"ctx": ctx, "base": base, "slots": 0, "off": SLOT_REGION, "size": slab_bytes, "keys": {}}
+
+    def _p2p_exchange(self, t, Lx, Ly, width, nvec, key):
+        from .mg import _stream
+        st = self.p2p
+        es = t.element_size()
+        row = Lx * width * es
+        k = (key, nvec, row)
+        if k not in st["keys"]:
+            need = ((nvec * row + 255) // 256) * 256
+            if st["off"] + 2 * need > st["size"] or (st["slots"] + 1) * 64 > SLOT_REGION:
+                raise MemoryError("P2P halo slab exhausted: raise MG2D_P2P_SLAB_MB")
+            st["keys"][k] = (st["slots"] * 64, st["off"], st["off"] + need)
+            st["slots"] += 1
+            st["off"] += 2 * need
+        slot, lo_off, hi_off = st["keys"][k]
+        b = st["base"]
+        me, pv, nx = b[self.rank], b[self.prev], b[self.next]
+        stride = Ly * Lx * width * es
+        st["ctx"].call("mg2d_halo_exchange", t.data_ptr(), t.data_ptr() + (Ly - 1) * row, stride, row, nvec,
+                       nx + lo_off, pv + hi_off, me + slot, pv + slot, nx + slot, _stream())
+        return _Ptr(me + lo_off), _Ptr(me + hi_off)
+
+    def p2p_errors(self, device) -> int:
+        """Number of exchanges that timed out waiting for a neighbour (0 = healthy)."""
+        if self.p2p is None:
+            return 0
+        n = self.p2p["slots"]
+        if n == 0:
+            return 0
+        buf = (ctypes.c_ulonglong * (8 * n))()
+        torch.cuda.synchronize()
+        import ctypes as C
+        cudart = C.CDLL("libcudart.so.12")
+        cudart.cudaMemcpy(buf, C.c_void_p(self.p2p["base"][self.rank]), C.c_size_t(64 * n), C.c_int(2))
+        return int(sum(buf[8 * i + 5] for i in range(n)))
+
+    def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None, as_tensor: bool = False):
         """Returns (lo, hi): the row below local row 0 (last row of rank-1) and the row above the last local row
         (first row of rank+1), periodic.  t: [Ly*Lx, width...] or a batch [nvec, Ly*Lx, width]."""
+        if self.p2p is not None and not as_tensor and t.is_cuda and (Lx * width * t.element_size()) % 16 == 0:
+            return self._p2p_exchange(t, Lx, Ly, width, nvec, key)
         if nvec == 1:
             first, last = t[:Lx], t[(Ly - 1) * Lx:Ly * Lx]
         else:
@@ -104,6 +174,8 @@ class DistMG(MG):
         for lv, (d, rows) in zip(self.LVL, self.plan):
             if d:
                 lv.set_strip(comm.rank * rows, rows)
+        if HALO_MODE == "p2p" and comm.p2p is None and comm.backend == "nccl" and comm.world > 1:
+            comm.enable_p2p(self.ctx, self.device)
 
     # field movement between a full host/device field and the strips
     def scatter_field(self, full: torch.Tensor) -> torch.Tensor:

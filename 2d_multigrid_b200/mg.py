@@ -121,7 +121,7 @@ class Level:
         assert self.lvl == 0
         self.U = U
         if self.distributed:   # link row below the strip: exchanged once
-            lo, _hi = mg.comm.exchange_rows(U, self.L, self.Ly, 2, 1, key=("U",))
+            lo, _hi = mg.comm.exchange_rows(U, self.L, self.Ly, 2, 1, key=("U",), as_tensor=True)
             self._U_lo = lo.clone()
             self.U_lo_ptr = self._U_lo.data_ptr()
         else:

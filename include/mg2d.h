@@ -158,6 +158,18 @@ int mg2d_minres_solve(mg2d_ctx*, const double* gram, const double* src, int ncop
 int mg2d_scale_phi(mg2d_ctx*, void* phi, void* e, long long estride, const double* a, int ncopies,
                    long long nelem, int dtype, void* stream);
 
+/* ---- multi-GPU strips: peer-to-peer halo exchange over NVLink (no reference counterpart) ------- */
+/* A slab of device memory other ranks can map (CUDA IPC): cudaMalloc + zero + 64-byte handle. */
+int mg2d_ipc_alloc(mg2d_ctx*, long long bytes, void** ptr, void* handle64);
+int mg2d_ipc_open(mg2d_ctx*, const void* handle64, void** ptr);
+/* One kernel = one halo exchange of a field's boundary rows with both strip neighbours: acknowledges the previous
+ * rows, waits for the neighbours' acknowledgements, stores `last` into next's lo buffer and `first` into prev's hi
+ * buffer through peer mappings, publishes the epoch (st.release.sys) and waits for the neighbours' rows.  Slots are
+ * 64-byte records {flag_lo, flag_hi, ack_prev, ack_next, epoch, error} inside the IPC slab. */
+int mg2d_halo_exchange(mg2d_ctx*, const void* first, const void* last, long long src_stride_bytes, long long row_bytes,
+                       int nvec, void* next_lo, void* prev_hi, void* slot_mine, void* slot_prev, void* slot_next,
+                       void* stream);
+
 /* ---- real scalar Laplace geometric MG, BASELINE config 1 (S2) -------------------------------------------- */
 /* relax (S2:46-72): num_iter lexicographic GS sweeps phi = scale (sum nbrs - b a^2), wavefront order. */
 int mg2d_s2_relax(mg2d_ctx*, double* phi, const double* b, int L, double scale, double a, int num_iter,

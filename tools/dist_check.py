@@ -50,6 +50,8 @@ for ug in (False, True):
         if rank == 0:
             print(f"  graph={ug} failed: {type(e).__name__}: {str(e)[:200]}", flush=True)
         break
+if rank == 0:
+    print(f"  halo mode {dmod.HALO_MODE} p2p active {comm.p2p is not None} p2p timeouts {comm.p2p_errors(dev)}", flush=True)
 t0 = time.time(); x1, i1 = mg2d.solve(ref, rhs=rhs, tol=1e-10, outer="gcr", use_graph=True, check_every=4); torch.cuda.synchronize()
 t0 = time.time(); x1, i1 = mg2d.solve(ref, rhs=rhs, tol=1e-10, outer="gcr", use_graph=True, check_every=4); torch.cuda.synchronize()
 if rank == 0:
