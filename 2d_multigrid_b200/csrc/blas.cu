@@ -408,36 +408,52 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned
     return false;
 }
 
-// first/last: this rank's boundary rows (nvec pieces of row_bytes, `src_stride` bytes apart);
-// peer_lo_of_next / peer_hi_of_prev: the neighbours' halo buffers; slots: mine and the two neighbours'.
-__global__ void __launch_bounds__(1024)
+// first/last: this rank's boundary rows (nvec pieces of row16 16-byte words, src_stride16 apart);
+// next_lo / prev_hi: the neighbours' halo buffers; slots: mine and the two neighbours'.
+// HX_CTAS CTAs share the copy; none depends on another one being resident (each spins on remote-written flags
+// only), the last CTA to finish its stores publishes the epoch and waits for the incoming rows.
+constexpr int HX_CTAS = 8;
+constexpr int HX_THREADS = 512;
+
+__global__ void __launch_bounds__(HX_THREADS)
 halo_exchange_kernel(const uint4* __restrict__ first, const uint4* __restrict__ last, long long src_stride16,
                      long long row16, int nvec, uint4* __restrict__ next_lo, uint4* __restrict__ prev_hi,
                      HaloSlot* mine, HaloSlot* prev, HaloSlot* next) {
     __shared__ unsigned long long s_epoch;
-    __shared__ int s_ok;
+    __shared__ int s_ok, s_last;
     if (threadIdx.x == 0) {
-        const unsigned long long e = mine->epoch;
+        const unsigned long long e = mine->epoch;     // only advanced after every CTA of this launch has arrived
         s_epoch = e;
-        st_release_sys(&prev->ack_next, e);      // I am prev's "next": its rows of epoch e (my lo_buf) are consumed
-        st_release_sys(&next->ack_prev, e);
+        if (blockIdx.x == 0) {
+            st_release_sys(&prev->ack_next, e);       // I am prev's "next": its rows of epoch e (my lo_buf) are consumed
+            st_release_sys(&next->ack_prev, e);
+        }
         s_ok = spin_until(&mine->ack_next, e) && spin_until(&mine->ack_prev, e);
     }
     __syncthreads();
     const unsigned long long e = s_epoch;
     if (s_ok) {
-        for (int v = 0; v < nvec; ++v)
-            for (long long k = threadIdx.x; k < row16; k += blockDim.x) {
-                next_lo[(size_t)v * row16 + k] = last[(size_t)v * src_stride16 + k];
-                prev_hi[(size_t)v * row16 + k] = first[(size_t)v * src_stride16 + k];
-            }
+        const long long total = (long long)nvec * row16;
+        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+            const long long v = k / row16, c = k - v * row16;
+            next_lo[k] = last[v * src_stride16 + c];
+            prev_hi[k] = first[v * src_stride16 + c];
+        }
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(&mine->pad[0], 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+        if (!s_ok) mine->error = 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence_system();
+        mine->pad[0] = 0;
         st_release_sys(&next->flag_lo, e + 1);
         st_release_sys(&prev->flag_hi, e + 1);
-        const bool ok = s_ok && spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
+        const bool ok = spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
         if (!ok) mine->error = 1;
         mine->epoch = e + 1;
     }
@@ -476,7 +492,7 @@ extern "C" int mg2d_halo_exchange(mg2d_ctx* ctx, const void* first, const void* 
     if (!first || !last || !next_lo || !prev_hi || !slot_mine || !slot_prev || !slot_next || nvec < 1 || row_bytes < 16 ||
         (row_bytes & 15) || (src_stride_bytes & 15))
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_halo_exchange: bad argument (rows must be multiples of 16 bytes)");
-    halo_exchange_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const uint4*)first, (const uint4*)last, src_stride_bytes / 16,
+    halo_exchange_kernel<<<(nvec * (row_bytes / 16) > 4096 ? HX_CTAS : 1), HX_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)first, (const uint4*)last, src_stride_bytes / 16,
         row_bytes / 16, nvec, (uint4*)next_lo, (uint4*)prev_hi, (HaloSlot*)slot_mine, (HaloSlot*)slot_prev, (HaloSlot*)slot_next);
     return mg2d_check_launch(ctx, "mg2d_halo_exchange");
 }
