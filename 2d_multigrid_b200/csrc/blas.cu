@@ -374,6 +374,123 @@ extern "C" int mg2d_axpy_ratio2(mg2d_ctx* ctx, void* y, const void* x, void* y2,
         "mg2d_axpy_ratio2");
 }
 
+// ---- fused updates of the outer flexible GCR (classical Gram-Schmidt against the stored directions) -------------
+// One pass each instead of 2 launches per stored direction: K1 all projections <W_j, w>; K2 w -= sum b_j W_j,
+// z -= sum b_j Z_j with |w|^2 and <w, r> of the NEW w accumulated on the fly; K3 x += a z, r -= a w with |r|^2.
+namespace {
+constexpr int GCR_MAXJ = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_dots_kernel(const cplx<T>* __restrict__ W, long long stride, int nj, const cplx<T>* __restrict__ w, long long n,
+                double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out) {
+    double red[2 * GCR_MAXJ];
+#pragma unroll
+    for (int k = 0; k < 2 * GCR_MAXJ; ++k) red[k] = 0.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const cplx<T> b = __ldg(w + e);
+#pragma unroll
+        for (int j = 0; j < GCR_MAXJ; ++j) {
+            if (j < nj) {
+                const cplx<T> a = __ldg(W + (size_t)j * stride + e);
+                red[2 * j] += (double)a.x * b.x + (double)a.y * b.y;
+                red[2 * j + 1] += (double)a.x * b.y - (double)a.y * b.x;
+            }
+        }
+    }
+    grid_reduce<2 * GCR_MAXJ, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_ortho_kernel(cplx<T>* __restrict__ w, cplx<T>* __restrict__ z, const cplx<T>* __restrict__ r,
+                 const cplx<T>* __restrict__ W, const cplx<T>* __restrict__ Z, long long stride, int nj,
+                 const double* __restrict__ dots, const double* __restrict__ wn2, long long n,
+                 double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out) {
+    using C = cplx<T>;
+    C beta[GCR_MAXJ];
+#pragma unroll
+    for (int j = 0; j < GCR_MAXJ; ++j) {
+        const double d = (j < nj) ? wn2[j] : 0.0;
+        beta[j] = (j < nj && d > 0.0) ? mk<T>((T)(-dots[2 * j] / d), (T)(-dots[2 * j + 1] / d)) : mk<T>(0, 0);
+    }
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C wv = w[e], zv = z[e];
+#pragma unroll
+        for (int j = 0; j < GCR_MAXJ; ++j) {
+            if (j < nj) {
+                cfma(wv, beta[j], __ldg(W + (size_t)j * stride + e));
+                cfma(zv, beta[j], __ldg(Z + (size_t)j * stride + e));
+            }
+        }
+        w[e] = wv; z[e] = zv;
+        const C rv = __ldg(r + e);
+        red[0] += (double)wv.x * wv.x + (double)wv.y * wv.y;
+        red[1] += (double)wv.x * rv.x + (double)wv.y * rv.y;       // <w, r> = conj(w) r
+        red[2] += (double)wv.x * rv.y - (double)wv.y * rv.x;
+    }
+    grid_reduce<4, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_step_kernel(cplx<T>* __restrict__ x, cplx<T>* __restrict__ r, const cplx<T>* __restrict__ z, const cplx<T>* __restrict__ w,
+                const double* __restrict__ wr, long long n, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                double* __restrict__ out) {
+    using C = cplx<T>;
+    const double d = wr[0];                       // wr = { |w|^2, Re<w,r>, Im<w,r> } as written by gcr_ortho_kernel
+    const C a = d > 0.0 ? mk<T>((T)(wr[1] / d), (T)(wr[2] / d)) : mk<T>(0, 0);
+    const C na = mk<T>(-a.x, -a.y);
+    double red[1] = {0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C xv = x[e], rv = r[e];
+        cfma(xv, a, __ldg(z + e));
+        cfma(rv, na, __ldg(w + e));
+        x[e] = xv; r[e] = rv;
+        red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+    }
+    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+}
+}  // namespace
+
+extern "C" int mg2d_gcr_dots(mg2d_ctx* ctx, const void* W, long long stride, int nj, const void* w, long long nelem, int dtype,
+                             double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!W || !w || !out || nj < 1 || nj > GCR_MAXJ || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_dots: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (gcr_dots_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)W, stride, nj, (const double2*)w, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_dots_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)W, stride, nj, (const float2*)w, nelem, ctx->partials, ctx->counter, out)),
+        "mg2d_gcr_dots");
+}
+
+extern "C" int mg2d_gcr_ortho(mg2d_ctx* ctx, void* w, void* z, const void* r, const void* W, const void* Z, long long stride, int nj,
+                              const double* dots, const double* wn2, long long nelem, int dtype, double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!w || !z || !r || !out || nj < 0 || nj > GCR_MAXJ || nelem < 1 || (nj > 0 && (!W || !Z || !dots || !wn2)))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_ortho: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (gcr_ortho_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)w, (double2*)z, (const double2*)r, (const double2*)W, (const double2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_ortho_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)w, (float2*)z, (const float2*)r, (const float2*)W, (const float2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out)),
+        "mg2d_gcr_ortho");
+}
+
+extern "C" int mg2d_gcr_step(mg2d_ctx* ctx, void* x, void* r, const void* z, const void* w, const double* wr, long long nelem,
+                             int dtype, double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || !r || !z || !w || !wr || !out || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_step: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (gcr_step_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, (double2*)r, (const double2*)z, (const double2*)w, wr, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_step_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, (float2*)r, (const float2*)z, (const float2*)w, wr, nelem, ctx->partials, ctx->counter, out)),
+        "mg2d_gcr_step");
+}
+
 // =========================================================================================================
 // Peer-to-peer halo exchange over NVLink (multi-GPU strips): ONE kernel per exchange that (1) tells both
 // neighbours their previous rows were consumed, (2) waits for the neighbours' acknowledgements, (3) stores

@@ -108,6 +108,100 @@ prolong_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const cplx<T>
     }
 }
 
+// ---- chirality-compacted projector (Wilson levels) -----------------------------------------------------------
+// f_near_null stores row d < nc/2 with only its first nf/2 columns non-zero and row d >= nc/2 with only the last nf/2
+// (S6/level.h:236-245); block normalisation and Gram-Schmidt keep that structure (rows of opposite chirality have
+// an exactly zero dot product).  Pc[s][i][j'] (nc x nf/2) keeps the non-zero half of every row, halving the bytes
+// streamed by restriction and prolongation.  Results equal the dense kernels (the dropped terms are x*0).
+template <int NF, int NC> struct TrGroupC {
+    static constexpr int HF = NF / 2;
+    static constexpr int E = HF * NC;
+    static constexpr int G = E < 32 ? E : 32;
+    static constexpr int ACC = E / G;
+};
+
+template <typename T, int NF, int NC>
+__global__ void __launch_bounds__(TR_THREADS)
+restrict_chiral_kernel(cplx<T>* __restrict__ vc, const cplx<T>* __restrict__ vf, const cplx<T>* __restrict__ Pc, AggGeom geo) {
+    using C = cplx<T>;
+    using TG = TrGroupC<NF, NC>;
+    constexpr int HF = TG::HF, E = TG::E, G = TG::G, ACC = TG::ACC, GPB = TR_THREADS / G;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const long long nagg = (long long)geo.Lxc * geo.Lyc;
+    const long long nsteps = (nagg + GPB - 1) / GPB;
+    const int nb = geo.block * geo.block;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long X = step * GPB + grp;
+        const bool active = X < nagg;
+        if (!active) X = nagg - 1;
+        const int yc = (int)(X / geo.Lxc), xc = (int)(X - (long long)yc * geo.Lxc);
+        C acc[ACC];
+#pragma unroll
+        for (int t = 0; t < ACC; ++t) acc[t] = mk<T>(0, 0);
+        for (int b = 0; b < nb; ++b) {
+            const size_t s = agg_site(geo, xc, yc, b);
+            const C* Ps = Pc + s * E;
+            const C v0 = __ldg(vf + s * NF + (g % HF)), v1 = __ldg(vf + s * NF + HF + (g % HF));
+#pragma unroll
+            for (int t = 0; t < ACC; ++t) {
+                const int i = (g + G * t) / HF;
+                cfma(acc[t], __ldg(Ps + g + G * t), (i >= NC / 2) ? v1 : v0);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < ACC; ++t) {
+            C a = acc[t];
+#pragma unroll
+            for (int m = 1; m < HF; m <<= 1) a = cadd(a, shfl_xor_c(a, m));
+            if (active && (g % HF) == 0) vc[(size_t)X * NC + (g + G * t) / HF] = a;
+        }
+    }
+}
+
+// accumulate != 0: vf += P^dagger vc ; accumulate == 0: vf = P^dagger vc (every fine site belongs to one aggregate)
+template <typename T, int NF, int NC>
+__global__ void __launch_bounds__(TR_THREADS)
+prolong_chiral_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const cplx<T>* __restrict__ Pc, AggGeom geo,
+                      int zero_vc, int accumulate) {
+    using C = cplx<T>;
+    using TG = TrGroupC<NF, NC>;
+    constexpr int HF = TG::HF, E = TG::E, G = TG::G, ACC = TG::ACC, GPB = TR_THREADS / G;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const long long nagg = (long long)geo.Lxc * geo.Lyc;
+    const long long nsteps = (nagg + GPB - 1) / GPB;
+    const int nb = geo.block * geo.block;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long X = step * GPB + grp;
+        const bool active = X < nagg;
+        if (!active) X = nagg - 1;
+        const int yc = (int)(X / geo.Lxc), xc = (int)(X - (long long)yc * geo.Lxc);
+        C w[ACC];
+#pragma unroll
+        for (int t = 0; t < ACC; ++t) w[t] = vc[(size_t)X * NC + (g + G * t) / HF];
+        for (int b = 0; b < nb; ++b) {
+            const size_t s = agg_site(geo, xc, yc, b);
+            const C* Ps = Pc + s * E;
+            C a0 = mk<T>(0, 0), a1 = mk<T>(0, 0);
+#pragma unroll
+            for (int t = 0; t < ACC; ++t) {
+                const int i = (g + G * t) / HF;
+                const C pv = __ldg(Ps + g + G * t);
+                if (i >= NC / 2) cfmac(a1, pv, w[t]); else cfmac(a0, pv, w[t]);
+            }
+#pragma unroll
+            for (int m = HF; m < G; m <<= 1) { a0 = cadd(a0, shfl_xor_c(a0, m)); a1 = cadd(a1, shfl_xor_c(a1, m)); }
+            if (active && g < HF) {
+                C* o0 = vf + s * NF + g; C* o1 = vf + s * NF + HF + g;
+                if (accumulate) { *o0 = cadd(*o0, a0); *o1 = cadd(*o1, a1); } else { *o0 = a0; *o1 = a1; }
+            }
+        }
+        if (zero_vc) {
+            __syncwarp();
+            if (active) for (int i = g; i < NC; i += G) vc[(size_t)X * NC + i] = mk<T>(0, 0);
+        }
+    }
+}
+
 // ---- setup kernels (runtime nf, nc) -------------------------------------------------------------------
 template <typename T>
 __global__ void pack_null_kernel(cplx<T>* __restrict__ P, const cplx<T>* __restrict__ V, int nvec, long long vstride,
@@ -303,6 +397,29 @@ int dispatch_transfer(mg2d_ctx* ctx, int which, void* vc, void* vf, const void* 
     return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_restrict/prolong: unsupported (nf, nc) pair");
 }
 
+template <typename T, int NF, int NC>
+int launch_transfer_c(mg2d_ctx* ctx, int which, void* vc, void* vf, const void* P, AggGeom geo, int zero_vc, int accumulate, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = TR_THREADS / TrGroupC<NF, NC>::G;
+    const long long nagg = (long long)geo.Lxc * geo.Lyc;
+    long long nb = (nagg + GPB - 1) / GPB;
+    if (nb > (long long)ctx->num_sms * 32) nb = (long long)ctx->num_sms * 32;
+    if (which == 0) restrict_chiral_kernel<T, NF, NC><<<(int)nb, TR_THREADS, 0, st>>>((C*)vc, (const C*)vf, (const C*)P, geo);
+    else prolong_chiral_kernel<T, NF, NC><<<(int)nb, TR_THREADS, 0, st>>>((C*)vf, (C*)vc, (const C*)P, geo, zero_vc, accumulate);
+    return mg2d_check_launch(ctx, which == 0 ? "mg2d_restrict_chiral" : "mg2d_prolong_chiral");
+}
+
+template <typename T>
+int dispatch_transfer_c(mg2d_ctx* ctx, int which, void* vc, void* vf, const void* P, int nf, int nc, AggGeom geo,
+                        int zero_vc, int accumulate, cudaStream_t st) {
+#define PAIR(NF, NC) if (nf == NF && nc == NC) return launch_transfer_c<T, NF, NC>(ctx, which, vc, vf, P, geo, zero_vc, accumulate, st)
+    PAIR(2, 4); PAIR(2, 8); PAIR(2, 16); PAIR(2, 32);
+    PAIR(4, 4); PAIR(8, 8); PAIR(16, 16); PAIR(32, 32);
+    PAIR(4, 8); PAIR(4, 16); PAIR(8, 16);
+#undef PAIR
+    return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_restrict/prolong_chiral: unsupported (nf, nc) pair");
+}
+
 inline int check_geom(mg2d_ctx* ctx, int Lxf, int Lyf, int block, int quad, const char* name) {
     if (Lxf < 1 || Lyf < 1 || block < 1 || quad < 1 || quad > 4 || Lxf % block || Lyf % block) {
         snprintf(ctx->err, sizeof(ctx->err), "%s: bad geometry (Lx=%d Ly=%d block=%d quad=%d)", name, Lxf, Lyf, block, quad);
@@ -404,4 +521,28 @@ extern "C" int mg2d_coarse_matrix(mg2d_ctx* ctx, void* Dc, const void* Df, const
         coarse_matrix_kernel<float><<<(int)nb, 256, smem, st>>>((float2*)Dc, (const float2*)Df, (const float2*)P, (const float2*)P_lo, (const float2*)P_hi, geo, nf, nc);
     } else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_coarse_matrix: bad dtype");
     return mg2d_check_launch(ctx, "mg2d_coarse_matrix");
+}
+
+extern "C" int mg2d_restrict_chiral(mg2d_ctx* ctx, void* vc, const void* vf, const void* Pc, int nf, int nc, int Lxf, int Lyf,
+                                    int block, int quad, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!vc || !vf || !Pc) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_restrict_chiral: null pointer");
+    if (int rc = check_geom(ctx, Lxf, Lyf, block, quad, "mg2d_restrict_chiral")) return rc;
+    AggGeom geo = make_geom(Lxf, Lyf, block, quad);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_transfer_c<double>(ctx, 0, vc, (void*)vf, Pc, nf, nc, geo, 0, 1, st);
+    if (dtype == MG2D_C64)  return dispatch_transfer_c<float>(ctx, 0, vc, (void*)vf, Pc, nf, nc, geo, 0, 1, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_restrict_chiral: bad dtype");
+}
+
+extern "C" int mg2d_prolong_chiral(mg2d_ctx* ctx, void* vf, void* vc, const void* Pc, int nf, int nc, int Lxf, int Lyf,
+                                   int block, int quad, int zero_vc, int accumulate, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!vc || !vf || !Pc) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_prolong_chiral: null pointer");
+    if (int rc = check_geom(ctx, Lxf, Lyf, block, quad, "mg2d_prolong_chiral")) return rc;
+    AggGeom geo = make_geom(Lxf, Lyf, block, quad);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_transfer_c<double>(ctx, 1, vc, vf, Pc, nf, nc, geo, zero_vc, accumulate, st);
+    if (dtype == MG2D_C64)  return dispatch_transfer_c<float>(ctx, 1, vc, vf, Pc, nf, nc, geo, zero_vc, accumulate, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_prolong_chiral: bad dtype");
 }

@@ -59,6 +59,7 @@ class Level:
         self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
         self.D0inv = None
         self.phi_null = None   # [S,nc,nf]
+        self.phi_null_c = None # [S,nc,nf/2]: chirality-compacted copy used by restriction / prolongation (wilson)
         self.U = None          # level 0 only: links [S,2]
         self.matrix_free = False
         self._work = {}
@@ -283,6 +284,17 @@ class Level:
         self.allreduce(out[:1], "max")
         return float(out[0].item())
 
+    def compact_projector(self, drop_dense: bool = False):
+        """Wilson levels: keep the non-zero chirality half of every row of phi_null (S6/level.h:236-245) in
+        phi_null_c[s][ic][jf'] so that restriction / prolongation stream half the bytes."""
+        if self.phi_null is None or self.mg.p.stencil != "wilson":
+            return
+        nc, nf = self.nc, self.n
+        P = self.phi_null
+        self.phi_null_c = torch.cat([P[:, :nc // 2, :nf // 2], P[:, nc // 2:, nf // 2:]], dim=1).contiguous()
+        if drop_dense:
+            self.phi_null = None
+
     def restriction(self, vec_c, vec_f, quad: int):
         """f_restriction (S6/near_null.h:217-240): vec_c = P vec_f."""
         mg = self.mg
@@ -292,26 +304,40 @@ class Level:
         dst = vec_c
         if gather:   # the coarse level is replicated: restrict the local strip, then all-gather the strips
             dst = self.work_coarse_strip()
-        mg.ctx.call("mg2d_restrict", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
-                    mg.p.block, quad, mg.dcode, _stream())
+        if self.phi_null_c is not None:
+            mg.ctx.call("mg2d_restrict_chiral", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null_c), self.n, self.nc, self.L,
+                        self.Ly, mg.p.block, quad, mg.dcode, _stream())
+        else:
+            mg.ctx.call("mg2d_restrict", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
+                        mg.p.block, quad, mg.dcode, _stream())
         if gather:
             mg.comm.allgather(vec_c, dst)
 
-    def prolongation(self, vec_f, vec_c, quad: int, zero_vc: bool = False):
-        """f_prolongation (S6/near_null.h:242-264): vec_f += P^dagger vec_c.  `self` is the FINE level."""
+    def prolongation(self, vec_f, vec_c, quad: int, zero_vc: bool = False, accumulate: bool = True):
+        """f_prolongation (S6/near_null.h:242-264): vec_f += P^dagger vec_c.  `self` is the FINE level.
+        accumulate=False writes vec_f = P^dagger vec_c (caller knows vec_f == 0; chirality-compacted path only)."""
         mg = self.mg
+        blk = mg.p.block
+
+        def launch(vc_ptr, zv):
+            if self.phi_null_c is not None:
+                mg.ctx.call("mg2d_prolong_chiral", _ptr(vec_f), vc_ptr, _ptr(self.phi_null_c), self.n, self.nc, self.L,
+                            self.Ly, blk, quad, zv, int(accumulate), mg.dcode, _stream())
+            else:
+                if not accumulate:
+                    mg.ctx.call("mg2d_zero", _ptr(vec_f), vec_f.numel(), mg.dcode, _stream())
+                mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), vc_ptr, _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
+                            blk, quad, zv, mg.dcode, _stream())
+
         if self.distributed and not self._coarse_distributed():
             # replicated coarse level: every rank prolongs from its rows of the full coarse field
-            blk = mg.p.block
             Lc = self.L // blk
             view = vec_c[(self.y0 // blk) * Lc:(self.y0 // blk + self.Ly // blk) * Lc]
-            mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(view), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
-                        blk, quad, 0, mg.dcode, _stream())
+            launch(_ptr(view), 0)
             if zero_vc:
                 mg.ctx.call("mg2d_zero", _ptr(vec_c), vec_c.numel(), mg.dcode, _stream())
             return
-        mg.ctx.call("mg2d_prolong_add", _ptr(vec_f), _ptr(vec_c), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
-                    mg.p.block, quad, int(zero_vc), mg.dcode, _stream())
+        launch(_ptr(vec_c), int(zero_vc))
 
     def _coarse_distributed(self) -> bool:
         nxt = self.mg.LVL[self.lvl + 1] if self.lvl + 1 < len(self.mg.LVL) else None
@@ -407,7 +433,9 @@ def make_single_precision(mg: "MG") -> "MG":
     c64 = torch.complex64
     for lv, l32 in zip(mg.LVL, m32.LVL):
         l32.phi, l32.r = l32.new_field(), l32.new_field()
-        if lv.phi_null is not None:
+        if lv.phi_null_c is not None:
+            l32.phi_null_c = lv.phi_null_c.to(c64)      # the cycle only needs the compacted projector
+        elif lv.phi_null is not None:
             l32.phi_null = lv.phi_null.to(c64)
         if lv.D is not None:
             l32.D = lv.D.to(c64)
@@ -494,6 +522,9 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
         raise FloatingPointError(f"near-null orthonormalisation failed (status {int(st[0])}): NaN or tiny norm "
                                  "(S6/modules_indiv.h:119-126, S6/near_null.h:149-159)")
     mg.info["ortho_worst"] = worst
+    if p.stencil == "wilson" and p.chiral_transfer:
+        for lvl in range(p.nlevels):
+            mg.LVL[lvl].compact_projector()
     if p.matrix_free:   # the stored level-0 operator was only needed for the Galerkin product
         mg.LVL[0].D = None
         mg.LVL[0].D0inv = None
@@ -507,24 +538,31 @@ def restriction_res(res_c, L_residue: Level, L_restrict: Level, quad: int):
     L_restrict.restriction(res_c, rtemp, quad)
 
 
-def prolongate_phi(phi_f, phi_c, LVLP: Level, quad: int):
+def prolongate_phi(phi_f, phi_c, LVLP: Level, quad: int, accumulate: bool = True):
     """f_prolongate_phi (S6/modules_main.h:243-252): phi_f += P^dagger phi_c ; phi_c = 0."""
-    LVLP.prolongation(phi_f, phi_c, quad, zero_vc=True)
+    LVLP.prolongation(phi_f, phi_c, quad, zero_vc=True, accumulate=accumulate)
 
 
-def MG_simple(mg: MG):
-    """f_MG_simple (S6/modules_main.h:255-280)."""
+def MG_simple(mg: MG, zero_start: bool = False):
+    """f_MG_simple (S6/modules_main.h:255-280).  p.pre / p.post give the sweeps per level (the reference uses one
+    count everywhere).  zero_start: the caller guarantees phi = 0 on every level at entry (preconditioner use);
+    a level without pre-smoothing then restricts r directly, since r - D*0 = r exactly."""
     p, LVL = mg.p, mg.LVL
     if p.nlevels > 0:
         for lvl in range(p.nlevels):
-            LVL[lvl].relax(p.n_smooth)
-            restriction_res(LVL[lvl + 1].r, LVL[lvl], LVL[lvl], p.quad)
+            LVL[lvl].relax(p.pre[lvl])
+            if zero_start and p.pre[lvl] == 0:
+                LVL[lvl].restriction(LVL[lvl + 1].r, LVL[lvl].r, p.quad)
+            else:
+                restriction_res(LVL[lvl + 1].r, LVL[lvl], LVL[lvl], p.quad)
         for lvl in range(p.nlevels, -1, -1):
-            LVL[lvl].relax(p.n_smooth)
+            LVL[lvl].relax(p.post[lvl])
             if lvl > 0:
-                prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad)
+                # phi of the finer level is still exactly zero when it was not pre-smoothed: overwrite, do not add
+                fresh = zero_start and p.pre[lvl - 1] == 0 and LVL[lvl - 1].phi_null_c is not None
+                prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad, accumulate=not fresh)
     else:
-        LVL[0].relax(p.n_smooth)
+        LVL[0].relax(p.post[0])
 
 
 def min_res(mg: MG, num_copies: int, level: int) -> torch.Tensor:
@@ -578,7 +616,7 @@ def MG_ntl(mg: MG):
     p, LVL, NTL = mg.p, mg.LVL, mg.NTL
     a = None
     for lvl in range(p.nlevels):
-        LVL[lvl].relax(p.n_smooth)
+        LVL[lvl].relax(p.pre[lvl])
         if lvl != p.nlevels - 1:
             restriction_res(LVL[lvl + 1].r, LVL[lvl], LVL[lvl], p.quad)
         else:
@@ -590,7 +628,7 @@ def MG_ntl(mg: MG):
         if lvl == p.nlevels:
             mg._ntl_fields(lvl - 1)
             for q in range(p.n_copies):
-                NTL[lvl][q].relax(p.n_smooth)
+                NTL[lvl][q].relax(p.post[lvl])
                 prolongate_phi(NTL[lvl - 1][q].phi, NTL[lvl][q].phi, NTL[lvl - 1][q], q + 1)
             if p.min_res_flag == 1:
                 a = min_res(mg, p.n_copies, lvl - 1)
@@ -600,7 +638,7 @@ def MG_ntl(mg: MG):
                 a[0:2 * p.n_copies:2] = 1.0 / p.n_copies
             scale_phi(mg, LVL[lvl - 1], a, p.n_copies, lvl - 1)
         else:
-            LVL[lvl].relax(p.n_smooth)
+            LVL[lvl].relax(p.post[lvl])
             if lvl > 0:
                 prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad)
     return a
@@ -610,8 +648,9 @@ class CycleGraph:
     """One multigrid cycle (f_MG_simple / f_MG_ntl) + the fused residual norm, captured into a CUDA graph so
     that a cycle costs one launch on the host.  Smoothers 'gs' (cooperative wavefront kernel) stay eager."""
 
-    def __init__(self, mg: MG, with_resmag: bool = True):
+    def __init__(self, mg: MG, with_resmag: bool = True, zero_start: bool = False):
         self.mg = mg
+        self.zero_start = zero_start
         self.ntl = mg.p.ntl and mg.p.nlevels > 0
         self.with_resmag = with_resmag
         self.graph = None
@@ -624,7 +663,7 @@ class CycleGraph:
         if self.ntl:
             self.weights = MG_ntl(mg)
         else:
-            MG_simple(mg)
+            MG_simple(mg, self.zero_start)
         if self.with_resmag:
             mg.LVL[0].residue_mag_async()
 
@@ -725,7 +764,9 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
     x, b = lv0.work("gcr_x"), lv0.work("gcr_b")
     r = lv0.work("gcr_r")
     Z, W = lv0.work("gcr_Z", restart), lv0.work("gcr_W", restart)
-    sc = lv0.dots("gcr")            # [0:2] dot, [2:4] <w,r>, [8+j] |w_j|^2, [4] |r|^2, [5] |b|^2
+    if restart > 8:
+        raise ValueError("restart <= 8 (mg2d_gcr_dots / mg2d_gcr_ortho handle up to 8 stored directions)")
+    sc = lv0.dots("gcr")            # [0:4] |w|^2,<w,r> ; [4] |r|^2 ; [5] |b|^2 ; [16:32] <W_j,w> ; [40+j] |w_j|^2
     call("mg2d_copy", _ptr(x), _ptr(lv0.phi), vs, dc, st())
     call("mg2d_copy", _ptr(b), _ptr(lv0.r), vs, dc, st())
     lv0._stencil(r, x, b, _lib.MODE_RESID, None)
@@ -739,38 +780,39 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
     if use_graph:
         cyc = pm.info.get("precond_graph")
         if cyc is None:
-            cyc = pm.info["precond_graph"] = CycleGraph(pm, with_resmag=False)
+            cyc = pm.info["precond_graph"] = CycleGraph(pm, with_resmag=False, zero_start=True)
     ntl = p.ntl and p.nlevels > 0
     info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
     hist = torch.zeros(max(check_every, 1), dtype=torch.float64, device=mg.device)
     bn2 = None
     it, slot = 0, 0
     done = False
+    fresh_top = p.nlevels > 0 and pm.p.pre[0] == 0 and pl0.phi_null_c is not None and not ntl
     while it < max_iters and not done:
         nb = min(check_every, max_iters - it)
         for k in range(nb):
-            # z = M(r): the cycle works on (LVL[0].phi, LVL[0].r)
-            pm.ctx.call("mg2d_zero", _ptr(pl0.phi), vs, pm.dcode, st())
+            # z = M(r): the cycle works on (LVL[0].phi, LVL[0].r) of the preconditioner hierarchy, from phi = 0
+            if not fresh_top:      # (with no pre-smoothing the first write to phi is the overwriting prolongation)
+                pm.ctx.call("mg2d_zero", _ptr(pl0.phi), vs, pm.dcode, st())
             pm.ctx.call("mg2d_convert", _ptr(pl0.r), pm.dcode, _ptr(r), dc, vs, st())
             if cyc is not None:
                 cyc.run()
             elif ntl:
                 MG_ntl(pm)
             else:
-                MG_simple(pm)
+                MG_simple(pm, zero_start=True)
             z, w = Z[slot], W[slot]
             pm.ctx.call("mg2d_convert", _ptr(z), dc, _ptr(pl0.phi), pm.dcode, vs, st())
             lv0._stencil(w, z, None, _lib.MODE_APPLY, None)
-            for j in range(slot):
-                call("mg2d_cdot_batch", _ptr(W[j]), vs, 1, _ptr(w), vs, 1, vs, dc, _ptr(sc), st())
-                mg.allreduce(sc[0:2])
-                call("mg2d_axpy_ratio2", _ptr(w), _ptr(W[j]), _ptr(z), _ptr(Z[j]), _ptr(sc), _ptr(sc[8 + j:]), -1.0, vs, dc, st())
-            call("mg2d_norm2", _ptr(w), vs, dc, _ptr(sc[8 + slot:]), st())
-            call("mg2d_cdot_batch", _ptr(w), vs, 1, _ptr(r), vs, 1, vs, dc, _ptr(sc[2:]), st())
-            mg.allreduce(sc[2:4]); mg.allreduce(sc[8 + slot:9 + slot])
-            call("mg2d_axpy_ratio2", _ptr(x), _ptr(z), None, None, _ptr(sc[2:]), _ptr(sc[8 + slot:]), 1.0, vs, dc, st())
-            call("mg2d_axpy_ratio2", _ptr(r), _ptr(w), None, None, _ptr(sc[2:]), _ptr(sc[8 + slot:]), -1.0, vs, dc, st())
-            call("mg2d_norm2", _ptr(r), vs, dc, _ptr(sc[4:]), st())
+            # classical Gram-Schmidt against the stored directions, then the minimal-residual step (3 fused passes)
+            if slot > 0:
+                call("mg2d_gcr_dots", _ptr(W), vs, slot, _ptr(w), vs, dc, _ptr(sc[16:]), st())
+                mg.allreduce(sc[16:16 + 2 * slot])
+            call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(r), _ptr(W), _ptr(Z), vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
+                 vs, dc, _ptr(sc[0:]), st())
+            mg.allreduce(sc[0:4])
+            sc[40 + slot:41 + slot].copy_(sc[0:1])                       # |w_slot|^2 for later projections
+            call("mg2d_gcr_step", _ptr(x), _ptr(r), _ptr(z), _ptr(w), _ptr(sc[0:]), vs, dc, _ptr(sc[4:]), st())
             mg.allreduce(sc[4:5])
             hist[k:k + 1].copy_(sc[4:5])
             slot += 1

@@ -35,6 +35,10 @@ class MGParams:
     dtype: str = "complex128"        # 'complex128' | 'complex64'
     mr_omega: float = 1.0
     min_res_flag: int = 1            # S6/modules_main.h:391
+    n_pre: object = None             # pre-smoothing sweeps: int or list per level (default n_smooth, as the reference)
+    n_post: object = None            # post-smoothing sweeps: int or list per level (default n_smooth); the coarsest
+                                     # level is relaxed once per cycle with n_post (S6/modules_main.h:270-273)
+    chiral_transfer: bool = True     # wilson: restriction / prolongation on the chirality-compacted projector
     matrix_free: bool | None = None  # level-0 Wilson operator applied from the links (no D0 stored).
                                      # default: True for smoother 'mr', False for 'gs'/'jacobi' (they need D0)
     size: list = field(default_factory=list)
@@ -63,6 +67,16 @@ class MGParams:
                 raise ValueError("lattice size must be divisible by the block size on every level")
             self.size.append(self.size[-1] // self.block)
             self.n_dof.append(self.n_dof_scale)
+        def per_level(v):
+            if v is None:
+                return [self.n_smooth] * (self.nlevels + 1)
+            if isinstance(v, int):
+                return [v] * (self.nlevels + 1)
+            v = list(v)
+            if len(v) != self.nlevels + 1:
+                raise ValueError("n_pre / n_post lists need one entry per level (nlevels + 1)")
+            return v
+        self.pre, self.post = per_level(self.n_pre), per_level(self.n_post)
         if self.matrix_free is None:
             self.matrix_free = self.stencil == "wilson" and self.smoother in ("mr", "rbgs")
         if self.matrix_free and (self.stencil != "wilson" or self.smoother not in ("mr", "rbgs")):

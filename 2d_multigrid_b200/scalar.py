@@ -102,3 +102,29 @@ def solve_scalar(L: int, m: float, nlevels: int, num_iters: int, t_flag: int = 0
         if resmag > 1e6:
             break
     return -1, mg.phi[0], hist
+
+
+def solve_scalar_s1(L: int, m: float, nlevels: int, num_iters: int, max_iters: int = 10000, res_threshold: float = 1.0e-14,
+                    device: int | None = None):
+    """main() of code/1_laplace_scalar/2D_laplace_Mgrid.cpp:111-215 (BASELINE configs[0]): the S2 operators with four
+    sources (:163), threshold 1e-14 (:122) and a way up that starts at level nlevels-1 (:181), so the coarsest level
+    is projected to but never relaxed.  Returns (iter [0-based, as printed by :189], phi_0, residual history)."""
+    mg = ScalarMG(L, m, nlevels, device)
+    for (x, y), v in (((0, 0), 1.0), ((1, 0), 2.0), ((2, 2), 5.0), ((3, 3), 7.5)):
+        mg.r[0][x + y * L] = v
+    hist = []
+    for it in range(max_iters):
+        for lvl in range(nlevels):
+            mg.relax(mg.phi[lvl], mg.r[lvl], lvl, num_iters)
+            mg.projection(mg.r[lvl + 1], mg.r[lvl], mg.phi[lvl], lvl, 1)
+        for lvl in range(nlevels - 1, -1, -1):
+            mg.relax(mg.phi[lvl], mg.r[lvl], lvl, num_iters)
+            if lvl > 0:
+                mg.interpolate(mg.phi[lvl - 1], mg.phi[lvl], lvl, 1)
+        resmag = mg.get_residue_mag(0)
+        hist.append(resmag)
+        if resmag < res_threshold:
+            return it, mg.phi[0], hist
+        if resmag > 1e6:
+            break
+    return -1, mg.phi[0], hist

@@ -104,6 +104,17 @@ int mg2d_axpy(mg2d_ctx*, void* y, const void* x, double a_re, double a_im, const
  * the device: the Gram-Schmidt and step updates of the outer GCR without a host round trip. */
 int mg2d_axpy_ratio2(mg2d_ctx*, void* y, const void* x, void* y2, const void* x2, const double* num,
                      const double* den, double sign, long long nelem, int dtype, void* stream);
+/* Outer flexible GCR (no reference counterpart), classical Gram-Schmidt against nj <= 8 stored
+ * directions W_j / Z_j (`stride` elements apart), one pass each:
+ *   mg2d_gcr_dots : out[2j..2j+1] = <W_j, w>
+ *   mg2d_gcr_ortho: w -= sum_j (dots_j / wn2_j) W_j ; z -= sum_j (...) Z_j ; out = { |w|^2, Re<w,r>, Im<w,r> } of the new w
+ *   mg2d_gcr_step : a = <w,r>/|w|^2 (wr = the three doubles above); x += a z ; r -= a w ; out[0] = |r|^2 */
+int mg2d_gcr_dots(mg2d_ctx*, const void* W, long long stride, int nj, const void* w, long long nelem, int dtype,
+                  double* out, void* stream);
+int mg2d_gcr_ortho(mg2d_ctx*, void* w, void* z, const void* r, const void* W, const void* Z, long long stride, int nj,
+                   const double* dots, const double* wn2, long long nelem, int dtype, double* out, void* stream);
+int mg2d_gcr_step(mg2d_ctx*, void* x, void* r, const void* z, const void* w, const double* wr, long long nelem,
+                  int dtype, double* out, void* stream);
 int mg2d_zero(mg2d_ctx*, void* x, long long nelem, int dtype, void* stream);
 int mg2d_copy(mg2d_ctx*, void* dst, const void* src, long long nelem, int dtype, void* stream);
 /* dst = src converted between MG2D_C128 and MG2D_C64 */
@@ -126,6 +137,15 @@ int mg2d_restrict(mg2d_ctx*, void* vc, const void* vf, const void* P, int nf, in
  * clears vc afterwards (f_prolongate_phi, S6/modules_main.h:243-252). */
 int mg2d_prolong_add(mg2d_ctx*, void* vf, void* vc, const void* P, int nf, int nc, int Lxf, int Lyf,
                      int block, int quad, int zero_vc, int dtype, void* stream);
+
+/* The same two operators on a chirality-compacted projector Pc[s][ic][jf'] (nc x nf/2): Level::f_near_null
+ * (S6/level.h:236-245) leaves row ic < nc/2 non-zero only in its first nf/2 columns and row ic >= nc/2 only in its
+ * last nf/2; Pc keeps that half.  Half the bytes, identical results.  accumulate = 0 writes vf = P^dagger vc
+ * (valid because every fine site belongs to exactly one aggregate) instead of adding. */
+int mg2d_restrict_chiral(mg2d_ctx*, void* vc, const void* vf, const void* Pc, int nf, int nc, int Lxf, int Lyf,
+                         int block, int quad, int dtype, void* stream);
+int mg2d_prolong_chiral(mg2d_ctx*, void* vf, void* vc, const void* Pc, int nf, int nc, int Lxf, int Lyf,
+                        int block, int quad, int zero_vc, int accumulate, int dtype, void* stream);
 
 /* ---- setup ---------------------------------------------------------------------------------------------- */
 /* Level::f_near_null tail (S6/level.h:217-246): P rows from the relaxed vectors V[v][s][nf]:

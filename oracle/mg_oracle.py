@@ -66,6 +66,8 @@ class Params:
     null_iters: int = 500     # S6/modules_main.h:193
     null_chunk: int = 4       # S6/level.h:190
     min_res_flag: int = 1     # S6/modules_main.h:391
+    n_pre: object = None      # ours: per-level pre / post sweep counts (int or list); default num_iters as the reference
+    n_post: object = None
     size: list = field(default_factory=list)
     n_dof: list = field(default_factory=list)
 
@@ -90,6 +92,12 @@ class Params:
             self.n_dof.append(self.n_dof_scale)
         if self.smoother is None:
             self.smoother = "gs" if self.gs_flag == 1 else "jacobi"
+
+        def per_level(v):
+            if v is None:
+                return [self.num_iters] * (self.nlevels + 1)
+            return [v] * (self.nlevels + 1) if isinstance(v, int) else list(v)
+        self.pre, self.post = per_level(self.n_pre), per_level(self.n_post)
 
     @property
     def diag(self) -> float:  # 1/scale[0], S6/params.h:76,82
@@ -524,14 +532,14 @@ def MG_simple(LVL, p: Params):
     """f_MG_simple, S6/modules_main.h:255-280."""
     if p.nlevels > 0:
         for lvl in range(p.nlevels):
-            LVL[lvl].smooth(p.size[lvl], p.num_iters, p)
+            LVL[lvl].smooth(p.size[lvl], p.pre[lvl], p)
             LVL[lvl + 1].r = restriction_res(LVL[lvl], LVL[lvl], lvl, p, p.quad)
         for lvl in range(p.nlevels, -1, -1):
-            LVL[lvl].smooth(p.size[lvl], p.num_iters, p)
+            LVL[lvl].smooth(p.size[lvl], p.post[lvl], p)
             if lvl > 0:
                 prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], lvl, p, p.quad)
     else:
-        LVL[0].smooth(p.size[0], p.num_iters, p)
+        LVL[0].smooth(p.size[0], p.post[0], p)
 
 
 def colpiv_householder_qr_solve(A: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -650,7 +658,7 @@ def gcr_MG(LVL, NTL, p: Params, b: np.ndarray, x0: np.ndarray | None = None, tol
            max_iters: int = 1000, restart: int = 8):
     """Flexible GCR(restart) with one multigrid cycle (from a zero start) as the preconditioner (ours: the
     reference only iterates the cycle stationarily, f_perform_MG).  Mirrored 1:1 by the CUDA driver.
-        z = M(r); w = D z; orthogonalise (w, z) against the stored (w_j, z_j) (modified Gram-Schmidt);
+        z = M(r); w = D z; orthogonalise (w, z) against the stored (w_j, z_j) (classical Gram-Schmidt);
         alpha = <w, r>/<w, w>; x += alpha z; r -= alpha w
     Returns (x, info)."""
     L0 = p.size[0]
@@ -673,8 +681,8 @@ def gcr_MG(LVL, NTL, p: Params, b: np.ndarray, x0: np.ndarray | None = None, tol
             MG_simple(LVL, p)
         z = lv0.phi
         w = lv0.apply_D(z, L0)
-        for zj, wj, wjn in zip(Z, W, [np.sum(np.abs(wj) ** 2) for wj in W]):
-            beta = np.vdot(wj, w) / wjn
+        betas = [np.vdot(wj, w) / np.sum(np.abs(wj) ** 2) for wj in W]      # classical Gram-Schmidt: all from the same w
+        for zj, wj, beta in zip(Z, W, betas):
             w = w - beta * wj
             z = z - beta * zj
         alpha = np.vdot(w, r) / np.sum(np.abs(w) ** 2)

@@ -83,6 +83,35 @@ def interpolate(phi_f, phi_c, lev, p, quad):
     phi_c[:] = 0.0
 
 
+def solve_s1(L, m, nlevels, num_iters, max_iters=10000, res_threshold=1.0e-14):
+    """main() of S1 = code/1_laplace_scalar/2D_laplace_Mgrid.cpp:111-215 (BASELINE configs[0] names this file).
+    Same operators as S2 (relax :51-66, f_projection :68-91, f_interpolate :93-109); differences: four sources
+    r[0][0][0]=1, r[0][1][0]=2, r[0][2][2]=5, r[0][3][3]=7.5 (:163, arrays are [x][y]), threshold 1e-14 (:122),
+    and the way up starts at level nlevels-1 (:181): the coarsest level receives a residual but is never relaxed.
+    Returns (iter [0-based, as printed by :189], phi_0, history)."""
+    p = S2Params(L, m, nlevels)
+    phi = [np.zeros(p.size[i] ** 2) for i in range(nlevels + 1)]
+    r = [np.zeros(p.size[i] ** 2) for i in range(nlevels + 1)]
+    for (x, y), v in (((0, 0), 1.0), ((1, 0), 2.0), ((2, 2), 5.0), ((3, 3), 7.5)):
+        r[0][x + y * L] = v
+    hist = []
+    for it in range(max_iters):
+        for lvl in range(nlevels):
+            relax(phi[lvl], r[lvl], lvl, num_iters, p)
+            r[lvl + 1] = projection(r[lvl], phi[lvl], lvl, p, 1)
+        for lvl in range(nlevels - 1, -1, -1):
+            relax(phi[lvl], r[lvl], lvl, num_iters, p)
+            if lvl > 0:
+                interpolate(phi[lvl - 1], phi[lvl], lvl, p, 1)
+        resmag = get_residue_mag(phi[0], r[0], 0, p)
+        hist.append(resmag)
+        if resmag < res_threshold:
+            return it, phi[0], hist
+        if resmag > 1e6:
+            break
+    return -1, phi[0], hist
+
+
 def solve(L, m, nlevels, num_iters, t_flag=0, max_iters=5000, res_threshold=1.0e-13, n_copies=2):
     """main() of S2 (:178-347).  Returns (iter [0-based, as printed], phi_0, residual history)."""
     p = S2Params(L, m, nlevels)

@@ -92,6 +92,43 @@ def test_config4_shape_small():
     assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-8
 
 
+def test_v04_cycle_chiral_transfer_parity():
+    """The bench cycle shape at a size the oracle follows: V(0,4) red-black cycle inside FGCR(8), 4x4 aggregates,
+    8 null vectors, chirality-compacted transfers and the overwrite-prolongation shortcut: same iteration count
+    and solution as the oracle (which uses the dense projector and no shortcut)."""
+    L = 64
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
+    b = np.zeros((L * L, 2), dtype=complex)
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    po = O.Params(L=L, num_iters=4, n_pre=0, n_post=4, block=4, m=-0.02, nlevels=2, null_iters=40, smoother="rbgs", n_dof_scale=16)
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=8)
+    p = mg2d.make_params(L, -0.02, nlevels=2, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=4, smoother="rbgs", null_iters=40)
+    mg = mg2d.setup(T(U), p)
+    assert mg.LVL[0].phi_null_c is not None and mg.LVL[0].matrix_free
+    for use_graph in (False, True):
+        x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=8, use_graph=use_graph)
+        assert ig["iters"] == io["iters"] and ig["true_resnorm"] < 1e-10
+        assert hist_close(ig["resnorms"], io["resnorms"], rtol=1e-6)
+        assert rel(x, xo) < 1e-7
+    # chiral kernels == dense kernels
+    lv = mg.LVL[0]
+    rng = np.random.default_rng(1)
+    vf = T(rng.normal(size=(L * L, 2)) + 1j * rng.normal(size=(L * L, 2)))
+    c1, c2 = torch.empty((256, 16), dtype=torch.complex128, device="cuda"), torch.empty((256, 16), dtype=torch.complex128, device="cuda")
+    lv.restriction(c1, vf, 1)
+    pc, lv.phi_null_c = lv.phi_null_c, None
+    lv.restriction(c2, vf, 1)
+    f1, f2, f3 = vf.clone(), vf.clone(), torch.full_like(vf, 7.0)
+    lv.prolongation(f2, c1.clone(), 1)
+    lv.phi_null_c = pc
+    lv.prolongation(f1, c1.clone(), 1)
+    lv.prolongation(f3, c1.clone(), 1, accumulate=False)
+    assert float((c1 - c2).abs().max()) < 1e-13 and float((f1 - f2).abs().max()) < 1e-13
+    assert float((f3 - (f1 - vf)).abs().max()) < 1e-13
+
+
 def test_gcr_outer_and_graph():
     L = 32
     U = O.gauge_gaussian(L, 0.3)
@@ -115,6 +152,31 @@ def test_gcr_outer_and_graph():
     m2 = mg2d.setup(T(U), p)
     x2, i2 = mg2d.solve(m2, use_graph=True)
     assert i1["iters"] == i2["iters"] and float((x1 - x2).abs().max()) < 1e-10
+
+
+def test_complex64_and_mixed_precision_solves():
+    """complex64 hierarchy (true residual ~1e-6 class) and the mixed-precision solve: complex64 V-cycle inside the
+    complex128 FGCR must reach the same 1e-10 TRUE residual (fp64 check) as the all-complex128 solve."""
+    L = 64
+    U = T(O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30)))
+    b = torch.zeros((L * L, 2), dtype=torch.complex128, device="cuda")
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    p = mg2d.make_params(L, 0.0, nlevels=2, block=4, n_null=4, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-10)
+    mg = mg2d.setup(U, p)
+    x64, i64 = mg2d.solve(mg, rhs=b, tol=1e-10, outer="gcr", use_graph=True)
+    xm, im = mg2d.solve(mg, rhs=b, tol=1e-10, outer="gcr", use_graph=True, precond_dtype="complex64")
+    assert i64["converged"] and im["converged"] and im["true_resnorm"] < 1e-10
+    assert abs(im["iters"] - i64["iters"]) <= 2
+    chk = torch.empty_like(xm)
+    mg.LVL[0].apply_D(chk, xm)
+    assert float(torch.linalg.vector_norm(chk - b)) < 1e-10
+    assert float((xm - x64).abs().max()) < 1e-8
+    # stand-alone complex64 hierarchy: converges to single-precision accuracy
+    p32 = mg2d.make_params(L, 0.0, nlevels=2, block=4, n_null=4, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-5, dtype="complex64")
+    m32 = mg2d.setup(U, p32)
+    x32, i32 = mg2d.solve(m32, rhs=b, tol=1e-5, outer="gcr")
+    assert i32["converged"]
+    assert float((x32.to(torch.complex128) - x64).abs().max()) < 1e-4 * float(x64.abs().max())
 
 
 def test_supplied_null_vectors_and_public_api():
@@ -155,6 +217,16 @@ def test_config1_scalar_laplace(args, want):
         assert it_g == want                                             # NB/2c...:587-598 golden numbers
     assert rel(phi_g, phi_o) < 1e-12
     assert abs(hist_g[0] / hist_o[0] - 1) < 1e-12
+
+
+@pytest.mark.parametrize("L,m,nl,ni,want", [(32, 0.1, 2, 3, 231), (32, 0.05, 3, 20, 31)])
+def test_config1_s1_variant(L, m, nl, ni, want):
+    """BASELINE configs[0] literally (code/1_laplace_scalar/2D_laplace_Mgrid.cpp): `want` is what the reference binary
+    prints ("Loop breaks at iteration N"), reproduced in tests/test_oracle_scalar.py::test_s1_variant_vs_binary."""
+    it_o, phi_o, _ = S2.solve_s1(L, m, nl, ni)
+    it_g, phi_g, _ = mg2d.solve_scalar_s1(L, m, nl, ni)
+    assert it_o == want and it_g == want
+    assert rel(phi_g, phi_o) < 1e-12
 
 
 # ---- full-size properties (no oracle run possible at these sizes) ----------------------------------------

@@ -54,3 +54,18 @@ def test_edge_cases():
         S.solve(8, 0.1, 3, 3)            # max_levels = log2(L)-1 (S2:218)
     it, phi, hist = S.solve(8, 0.5, 2, 3)
     assert it >= 0 and hist[-1] < 1e-13
+
+
+@pytest.mark.parametrize("L,m,nl,ni", [(32, 0.1, 2, 3), (32, 0.05, 3, 20)])
+def test_s1_variant_vs_binary(repo_root, L, m, nl, ni):
+    """BASELINE configs[0] literally: code/1_laplace_scalar/2D_laplace_Mgrid.cpp (hard-coded constants patched at
+    build time by oracle/Makefile) against oracle.scalar_s2.solve_s1."""
+    exe = os.path.join(repo_root, "oracle", "_ref", f"s1_mgrid_L{L}_m{m}_n{nl}_i{ni}")
+    if not os.path.exists(exe) and os.path.isdir("/root/reference"):
+        subprocess.call(["make", "-C", os.path.join(repo_root, "oracle"), f"_ref/s1_mgrid_L{L}_m{m}_n{nl}_i{ni}"])
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref S1 binary not built (needs /root/reference)")
+    out = subprocess.run([exe], capture_output=True, text=True).stdout
+    want = int(re.search(r"Loop breaks at iteration (\d+)", out).group(1))
+    got, _, hist = S.solve_s1(L, m, nl, ni)
+    assert got == want

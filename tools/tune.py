@@ -1,0 +1,49 @@
+"""Cycle-shape tuning on one GPU: pre/post smoothing counts per level, same hierarchy."""
+import os, sys, time, math
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mg2d, bench
+from importlib import import_module
+critical = import_module("2d_multigrid_b200.critical")
+torch.cuda.set_device(0); dev = torch.device("cuda", 0)
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=60, seed=1234, device="cuda"); U = torch.exp(1j * th).to(torch.complex128); del th
+mcrit = {4096: -0.06552, 1024: -0.06838}.get(L)
+if mcrit is None:
+    mcrit, _ = critical.estimate_critical_mass(U, lambda m: bench.workload_params(mg2d, L, m), iters=4, refine=3)
+p = bench.workload_params(mg2d, L, mcrit + 1e-3)
+mg = mg2d.setup(U, p, init="device")
+rhs = torch.zeros((L * L, 2), dtype=torch.complex128, device=dev); rhs[L // 2 + (L // 2) * L, 0] = 1.0
+nl = p.nlevels
+def run(pre, post, mixed, restart=8):
+    for m in [mg] + ([mg.info["single"]] if "single" in mg.info else []):
+        m.p.pre, m.p.post = list(pre), list(post)
+        m.info.pop("precond_graph", None); m.info.pop("cycle_graph", None)
+    kw = dict(rhs=rhs, tol=1e-10, outer="gcr", restart=restart, use_graph=True, check_every=4, max_iters=120)
+    if mixed: kw["precond_dtype"] = "complex64"
+    x, info = mg2d.solve(mg, **kw)
+    if mixed:   # the shadow was created with the default counts on first use: re-apply and re-run
+        m = mg.info["single"]; m.p.pre, m.p.post = list(pre), list(post); m.info.pop("precond_graph", None)
+        x, info = mg2d.solve(mg, **kw)
+    torch.cuda.synchronize(); t0 = time.time()
+    x, info = mg2d.solve(mg, **kw)
+    torch.cuda.synchronize(); return info, (time.time() - t0) * 1e3
+configs = [
+    ("V(4,4) all", [4] * (nl + 1), [4] * (nl + 1)),
+    ("V(2,2) all", [2] * (nl + 1), [2] * (nl + 1)),
+    ("V(0,4) all", [0] * (nl + 1), [4] * (nl + 1)),
+    ("V(0,6) all", [0] * (nl + 1), [6] * (nl + 1)),
+    ("V(0,8) all", [0] * (nl + 1), [8] * (nl + 1)),
+    ("V(1,3) all", [1] * (nl + 1), [3] * (nl + 1)),
+    ("l0 (4,4) l1 (2,2) rest (4,4)", [4, 2] + [4] * (nl - 1), [4, 2] + [4] * (nl - 1)),
+    ("l0 (2,2) l1 (2,2) rest (4,4)", [2, 2] + [4] * (nl - 1), [2, 2] + [4] * (nl - 1)),
+    ("l0 (0,6) l1 (0,4) rest (4,4)", [0, 0] + [4] * (nl - 1), [6, 4] + [4] * (nl - 1)),
+    ("l0 (0,4) l1 (0,3) rest (4,8)", [0, 0] + [4] * (nl - 1), [4, 3] + [8] * (nl - 1)),
+    ("l0 (0,8) l1 (0,4) rest (0,8)", [0] * (nl + 1), [8, 4] + [8] * (nl - 1)),
+]
+for name, pre, post in configs:
+    out = []
+    for mixed in (False, True):
+        info, ms = run(pre, post, mixed)
+        out.append(f"{'c64pc' if mixed else 'c128 '}: {info['iters']:3d} it {ms:7.1f} ms conv {info['converged']} true {info['true_resnorm']:.1e}")
+    print(f"{name:34s} | " + " | ".join(out), flush=True)
