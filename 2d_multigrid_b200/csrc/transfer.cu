@@ -202,6 +202,47 @@ prolong_chiral_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const 
     }
 }
 
+// Level 0 -> Wilson spinors (NF = 2) with 4x4 aggregates and NC coarse dof: the generic lane mapping needs a
+// log2(NC)-step butterfly per fine site (shuffle-bound: 32 SHFL per 512 B streamed).  Here a warp owns one aggregate,
+// streams Pc coalesced exactly as before, parks the products conj(Pc[s][i]) * vc[i] in a padded shared-memory tile
+// [16 sites][NC] and then lane (site b, chirality c) adds its NC/2 terms: no shuffles, 2 x 4 KB of shared traffic
+// per 4 KB of DRAM traffic.
+template <typename T, int NC>
+__global__ void __launch_bounds__(TR_THREADS)
+prolong_chiral_nf2_blk4_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const cplx<T>* __restrict__ Pc, AggGeom geo,
+                               int zero_vc, int accumulate) {
+    using C = cplx<T>;
+    constexpr int NB = 16, PAD = NC + 1, WPB = TR_THREADS / 32, SPP = 32 / NC;   // SPP sites per pass of the warp
+    static_assert(NC == 16 || NC == 8, "NC");
+    __shared__ C tile[WPB][NB * PAD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    C* tl = tile[warp];
+    const long long nagg = (long long)geo.Lxc * geo.Lyc;
+    const int i = lane % NC, sub = lane / NC;
+    for (long long X = (long long)blockIdx.x * WPB + warp; X < nagg; X += (long long)gridDim.x * WPB) {
+        const int yc = (int)(X / geo.Lxc), xc = (int)(X - (long long)yc * geo.Lxc);
+        const C w = vc[(size_t)X * NC + i];
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += SPP) {
+            const int b = b0 + sub;
+            const size_t s = agg_site(geo, xc, yc, b);
+            tl[b * PAD + i] = cmulc(__ldg(Pc + s * NC + i), w);      // conj(P) * vc
+        }
+        __syncwarp();
+        {   // lane = (site b, chirality c)
+            const int b = lane >> 1, c = lane & 1;
+            C a = mk<T>(0, 0);
+#pragma unroll
+            for (int k = 0; k < NC / 2; ++k) a = cadd(a, tl[b * PAD + c * (NC / 2) + k]);
+            const size_t s = agg_site(geo, xc, yc, b);
+            C* o = vf + s * 2 + c;
+            if (accumulate) *o = cadd(*o, a); else *o = a;
+        }
+        __syncwarp();
+        if (zero_vc && lane < NC) vc[(size_t)X * NC + lane] = mk<T>(0, 0);
+    }
+}
+
 // ---- setup kernels (runtime nf, nc) -------------------------------------------------------------------
 template <typename T>
 __global__ void pack_null_kernel(cplx<T>* __restrict__ P, const cplx<T>* __restrict__ V, int nvec, long long vstride,
@@ -405,7 +446,17 @@ int launch_transfer_c(mg2d_ctx* ctx, int which, void* vc, void* vf, const void* 
     long long nb = (nagg + GPB - 1) / GPB;
     if (nb > (long long)ctx->num_sms * 32) nb = (long long)ctx->num_sms * 32;
     if (which == 0) restrict_chiral_kernel<T, NF, NC><<<(int)nb, TR_THREADS, 0, st>>>((C*)vc, (const C*)vf, (const C*)P, geo);
-    else prolong_chiral_kernel<T, NF, NC><<<(int)nb, TR_THREADS, 0, st>>>((C*)vf, (C*)vc, (const C*)P, geo, zero_vc, accumulate);
+    else {
+        if constexpr (NF == 2 && (NC == 8 || NC == 16)) {
+            if (geo.block == 4) {
+                long long nw = (nagg + TR_THREADS / 32 - 1) / (TR_THREADS / 32);
+                if (nw > (long long)ctx->num_sms * 32) nw = (long long)ctx->num_sms * 32;
+                prolong_chiral_nf2_blk4_kernel<T, NC><<<(int)nw, TR_THREADS, 0, st>>>((C*)vf, (C*)vc, (const C*)P, geo, zero_vc, accumulate);
+                return mg2d_check_launch(ctx, "mg2d_prolong_chiral");
+            }
+        }
+        prolong_chiral_kernel<T, NF, NC><<<(int)nb, TR_THREADS, 0, st>>>((C*)vf, (C*)vc, (const C*)P, geo, zero_vc, accumulate);
+    }
     return mg2d_check_launch(ctx, which == 0 ? "mg2d_restrict_chiral" : "mg2d_prolong_chiral");
 }
 

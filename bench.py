@@ -357,9 +357,11 @@ def main():
         t_ap1 = time_kernel(lambda: l1.apply_D(d_, c), 10, flush if l1.S * n1 * n1 * 80 < 2e8 else None)
         kern.append((f"stencil_kernel<double,{n1}> (coarse D-apply, level 1)", (5 * n1 * n1 + 2 * n1) * 16.0 * l1.S, t_ap1))
         t_res = time_kernel(lambda: lv0.restriction(l1.r, a, 1), 10, flush)
-        kern.append((f"restrict_kernel<double,2,{n1}> (level 0->1)", ((n1 * 2 + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
+        chiral = lv0.phi_null_c is not None          # compacted projector: nc x nf/2 per fine site
+        pb = n1 * (1 if chiral else 2)
+        kern.append((f"restrict{'_chiral' if chiral else ''}_kernel<double,2,{n1}> (level 0->1)", ((pb + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
         t_pro = time_kernel(lambda: lv0.prolongation(b_, l1.phi, 1), 10, flush)
-        kern.append((f"prolong_kernel<double,2,{n1}> (level 1->0)", ((n1 * 2 + 2 * 2) * 16.0 + n1 * 16.0 / 16) * S0, t_pro))
+        kern.append((f"prolong{'_chiral' if chiral else ''}_kernel<double,2,{n1}> (level 1->0, accumulate)", ((pb + 2 * 2) * 16.0 + n1 * 16.0 / 16) * S0, t_pro))
     barrier()
     if rank != 0:
         _finish(comm)

@@ -257,7 +257,7 @@ def test_fullsize_properties_1024():
     omy = torch.roll(om.reshape(L, L), -1, 0).reshape(-1)
     U2 = torch.stack([om * U[:, 0] * omx.conj(), om * U[:, 1] * omy.conj()], 1).contiguous()
     lv2 = mg2d.MG(mg2d.make_params(L, -0.02, nlevels=0, smoother="rbgs")).LVL[0]
-    lv2.U, lv2.matrix_free = U2, True
+    lv2.compute_lvl0_matrix(U2, store=False)          # links only: matrix-free operator
     out2 = torch.empty_like(v)
     lv2.apply_D(out2, om[:, None] * v)
     assert float((out2 - om[:, None] * Dv).abs().max()) < 1e-11

@@ -92,7 +92,7 @@ for Lb in (1024, 4096):
     pb = mg2d.make_params(Lb, 0.01, nlevels=0, smoother="mr")
     mb = mg2d.MG(pb)
     Ub = torch.exp(1j * torch.randn(Lb * Lb, 2, dtype=torch.float64, device=dev) * 0.2).to(torch.complex128)
-    lv = mb.LVL[0]; lv.U = Ub; lv.matrix_free = True
+    lv = mb.LVL[0]; lv.compute_lvl0_matrix(Ub, store=False)
     a = torch.randn(Lb * Lb, 2, dtype=torch.complex128, device=dev); b = torch.empty_like(a)
     for _ in range(3): lv.apply_D(b, a)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
