@@ -57,6 +57,7 @@ restrict_kernel(cplx<T>* __restrict__ vc, const cplx<T>* __restrict__ vf, const 
         C acc[ACC];
 #pragma unroll
         for (int t = 0; t < ACC; ++t) acc[t] = mk<T>(0, 0);
+#pragma unroll 4
         for (int b = 0; b < nb; ++b) {
             const size_t s = agg_site(geo, xc, yc, b);
             const C v = __ldg(vf + s * NF + (g % NF));
@@ -91,6 +92,7 @@ prolong_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const cplx<T>
         C w[ACC];
 #pragma unroll
         for (int t = 0; t < ACC; ++t) w[t] = vc[(size_t)X * NC + (g + G * t) / NF];
+#pragma unroll 4
         for (int b = 0; b < nb; ++b) {
             const size_t s = agg_site(geo, xc, yc, b);
             const C* Ps = P + s * E;
@@ -138,6 +140,7 @@ restrict_chiral_kernel(cplx<T>* __restrict__ vc, const cplx<T>* __restrict__ vf,
         C acc[ACC];
 #pragma unroll
         for (int t = 0; t < ACC; ++t) acc[t] = mk<T>(0, 0);
+#pragma unroll 4
         for (int b = 0; b < nb; ++b) {
             const size_t s = agg_site(geo, xc, yc, b);
             const C* Ps = Pc + s * E;
@@ -178,6 +181,7 @@ prolong_chiral_kernel(cplx<T>* __restrict__ vf, cplx<T>* __restrict__ vc, const 
         C w[ACC];
 #pragma unroll
         for (int t = 0; t < ACC; ++t) w[t] = vc[(size_t)X * NC + (g + G * t) / HF];
+#pragma unroll 4
         for (int b = 0; b < nb; ++b) {
             const size_t s = agg_site(geo, xc, yc, b);
             const C* Ps = Pc + s * E;
