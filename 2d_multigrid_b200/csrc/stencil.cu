@@ -12,6 +12,7 @@
 // shuffles.  Algorithmic traffic per site (c128): apply (5n^2+2n)*16 B, relax (5n^2+3n)*16 B (+n^2*16 D0inv).
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -159,6 +160,86 @@ stencil_rb_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx
         C o = apply_minus_inv<T, N, G>(Dinv + s * N * N, acc, g);
         if (active && jp == 0) phi[s * N + i] = o;
     }
+}
+
+// Red-black half sweep for the complex64 preconditioner hierarchy with the operator blocks stored in HALF precision
+// (`__half2` = (re,im), same [s][k][j][i] order; arithmetic and fields stay fp32).  The stored operator is the dominant
+// HBM traffic of a cycle (4 hop blocks + D0inv per updated site), so halving its bytes again is the remaining lever once the
+// fp32 kernel sits at the roofline.  One warp per site; every lane loads 16 bytes = 4 consecutive rows i of one column j,
+// keeps 4 accumulators, partial sums meet in log2(128/N) butterfly steps; the intermediate vector goes through 128 B of
+// shared memory for the D0inv product.  N in {8, 16, 32}.
+template <int N>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_h_kernel(float2* phi, const float2* lo, const float2* hi, const __half2* __restrict__ Dh,
+                    const __half2* __restrict__ Dinvh, const float2* __restrict__ r, int Lx, int Ly, int colour, int yoff) {
+    constexpr int WPB = ST_THREADS / 32;
+    constexpr int HOP_CHUNKS = 4 * N * N / 4, INV_CHUNKS = N * N / 4;      // 16-byte chunks (4 elements) per site
+    constexpr int KJ_STEP = 128 / N;                                        // (k,j) advance per 32-lane step
+    __shared__ float2 s_w[WPB][N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = (4 * lane) % N, kj0 = (4 * lane) / N;
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    for (long long h = (long long)blockIdx.x * WPB + warp; h < S2; h += (long long)gridDim.x * WPB) {
+        const int y = (int)(h / Lh);
+        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        const size_t s = (size_t)y * Lx + x;
+        const uint4* Hs = reinterpret_cast<const uint4*>(Dh + s * 5 * N * N + N * N);   // hop blocks k = 1..4
+        float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int t = 0; t < HOP_CHUNKS / 32; ++t) {
+            const int kj = kj0 + KJ_STEP * t;
+            const int k = 1 + kj / N, j = kj % N;
+            const uint4 raw = __ldg(Hs + lane + 32 * t);
+            const float2 v = __ldcg(nbr_ptr<float2>(phi, lo, hi, k, x, y, Lx, Ly, N) + j);
+            const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cfma(acc[q], __half22float2(hp[q]), v);
+        }
+#pragma unroll
+        for (int m = N / 4; m < 32; m <<= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = cadd(acc[q], shfl_xor_c(acc[q], m));
+        if (lane < N / 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float2 w = acc[q];
+                if (r) w = csub(w, __ldg(r + s * N + i0 + q));
+                s_w[warp][i0 + q] = w;
+            }
+        }
+        __syncwarp();
+        const uint4* Is = reinterpret_cast<const uint4*>(Dinvh + s * N * N);
+        float2 out[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int t = 0; t < (INV_CHUNKS + 31) / 32; ++t) {
+            const int c = lane + 32 * t;
+            if (c < INV_CHUNKS) {
+                const int j = kj0 + KJ_STEP * t;
+                const uint4 raw = __ldg(Is + c);
+                const float2 wj = s_w[warp][j];
+                const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cfma(out[q], __half22float2(hp[q]), wj);
+            }
+        }
+#pragma unroll
+        for (int m = N / 4; m < 32; m <<= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = cadd(out[q], shfl_xor_c(out[q], m));
+        if (lane < N / 4) {
+            float4* dst = reinterpret_cast<float4*>(phi + s * N + i0);
+            dst[0] = make_float4(-out[0].x, -out[0].y, -out[1].x, -out[1].y);
+            dst[1] = make_float4(-out[2].x, -out[2].y, -out[3].x, -out[3].y);
+        }
+        __syncwarp();
+    }
+}
+
+// (re,im) fp32 pairs -> __half2, elementwise (builds the half-precision copy of D / D0inv)
+__global__ void to_half_kernel(__half2* __restrict__ dst, const float2* __restrict__ src, long long n) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dst[e] = __float22half2_rn(__ldg(src + e));
 }
 
 // lexicographic Gauss-Seidel by anti-diagonal wavefronts (cooperative launch, grid.sync between fronts)
@@ -433,4 +514,33 @@ extern "C" int mg2d_relax_rb(mg2d_ctx* ctx, void* phi, const void* phi_lo, const
     if (dtype == MG2D_C128) return dispatch_rb<double>(ctx, n, phi, phi_lo, phi_hi, D, D0inv, r, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
     if (dtype == MG2D_C64)  return dispatch_rb<float>(ctx, n, phi, phi_lo, phi_hi, D, D0inv, r, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb: bad dtype");
+}
+
+extern "C" int mg2d_to_half(mg2d_ctx* ctx, void* dst_half2, const void* src_c64, long long nelem, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!dst_half2 || !src_c64 || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_to_half: bad argument");
+    long long nb = (nelem + 255) / 256; if (nb > (long long)ctx->num_sms * 16) nb = (long long)ctx->num_sms * 16;
+    to_half_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>((__half2*)dst_half2, (const float2*)src_c64, nelem);
+    return mg2d_check_launch(ctx, "mg2d_to_half");
+}
+
+extern "C" int mg2d_relax_rb_half(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* Dh,
+                                  const void* D0invh, const void* r, int n, int Lx, int Ly, int colour, int yoff, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !Dh || !D0invh || Lx < 2 || (Lx & 1) || Ly < 1 || (colour != 0 && colour != 1))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_half: bad argument (Lx must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long S2 = (long long)(Lx / 2) * Ly;
+    long long nb = (S2 + ST_THREADS / 32 - 1) / (ST_THREADS / 32);
+    if (nb > (long long)ctx->num_sms * 32) nb = (long long)ctx->num_sms * 32;
+#define RBH(N) stencil_rb_h_kernel<N><<<(int)nb, ST_THREADS, 0, st>>>((float2*)phi, (const float2*)phi_lo, (const float2*)phi_hi, \
+        (const __half2*)Dh, (const __half2*)D0invh, (const float2*)r, Lx, Ly, colour, yoff)
+    switch (n) {
+        case 8: RBH(8); break;
+        case 16: RBH(16); break;
+        case 32: RBH(32); break;
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb_half: n_dof must be 8, 16 or 32");
+    }
+#undef RBH
+    return mg2d_check_launch(ctx, "mg2d_relax_rb_half");
 }

@@ -58,6 +58,8 @@ class Level:
         self.r = None
         self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
         self.D0inv = None
+        self.Dh = None         # optional half-precision copies (__half2) of D / D0inv for the complex64 preconditioner
+        self.D0inv_h = None
         self.phi_null = None   # [S,nc,nf]
         self.phi_null_c = None # [S,nc,nf/2]: chirality-compacted copy used by restriction / prolongation (wilson)
         self.U = None          # level 0 only: links [S,2]
@@ -175,6 +177,18 @@ class Level:
         d = self.residue_mag_async().cpu()
         return math.sqrt(d[0].item()) / math.sqrt(d[3].item())
 
+    def make_half_blocks(self):
+        """__half2 copies of the stored operator and of D0^-1 (complex64 levels with n in {8,16,32}) for
+        mg2d_relax_rb_half."""
+        if self.D is None or self.mg.p.dtype != "complex64" or self.n not in (8, 16, 32):
+            return
+        self._ensure_D0inv()
+        mg = self.mg
+        self.Dh = torch.empty(self.D.shape, dtype=torch.float32, device=mg.device)            # 4 bytes per complex
+        self.D0inv_h = torch.empty(self.D0inv.shape, dtype=torch.float32, device=mg.device)
+        mg.ctx.call("mg2d_to_half", _ptr(self.Dh), _ptr(self.D), self.D.numel(), _stream())
+        mg.ctx.call("mg2d_to_half", _ptr(self.D0inv_h), _ptr(self.D0inv), self.D0inv.numel(), _stream())
+
     def _ensure_D0inv(self):
         if self.D0inv is None:
             if self.D is None:
@@ -233,6 +247,10 @@ class Level:
                             lo, hi = self._halo(ph)
                             mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(rv),
                                         float(mg.p.mass), self.L, self.Ly, colour, self.y0 & 1, mg.dcode, _stream())
+                    elif self.Dh is not None and nvec == 1:
+                        lo, hi = self._halo(phi)
+                        mg.ctx.call("mg2d_relax_rb_half", _ptr(phi), lo, hi, _ptr(self.Dh), _ptr(self.D0inv_h), _ptr(r),
+                                    self.n, self.L, self.Ly, colour, self.y0 & 1, _stream())
                     else:
                         self._ensure_D0inv()
                         lo, hi = self._halo(phi, nvec)
@@ -417,7 +435,7 @@ class MG:
         lv0.compute_lvl0_matrix(U, store=True)
 
 
-def make_single_precision(mg: "MG") -> "MG":
+def make_single_precision(mg: "MG", half_blocks: bool = False) -> "MG":
     """complex64 shadow of a set-up hierarchy (links, stored operators, projectors), used as the preconditioner
     of the fp64 outer GCR: every V-cycle kernel then moves half the bytes.  The outer residual, the GCR vectors
     and the convergence test stay in complex128, so the 1e-10 TRUE residual is unaffected."""
@@ -447,6 +465,8 @@ def make_single_precision(mg: "MG") -> "MG":
                 l32.U_lo_ptr = l32._U_lo.data_ptr()
             else:
                 l32.U_lo_ptr = l32.U.data_ptr() + (l32.Ly - 1) * l32.L * 2 * l32.U.element_size()
+        if half_blocks:
+            l32.make_half_blocks()
     return m32
 
 

@@ -92,6 +92,13 @@ int mg2d_wilson_relax_rb(mg2d_ctx*, void* phi, const void* phi_lo, const void* p
                          const void* U_lo, const void* r, double mass, int Lx, int Ly, int colour, int yoff,
                          int dtype, void* stream);
 
+/* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
+ * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64
+ * operator); fields and arithmetic stay fp32.  n in {8,16,32}.  Mixed-precision option, no reference counterpart. */
+int mg2d_relax_rb_half(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* Dh, const void* D0invh,
+                       const void* r, int n, int Lx, int Ly, int colour, int yoff, void* stream);
+int mg2d_to_half(mg2d_ctx*, void* dst_half2, const void* src_c64, long long nelem, void* stream);
+
 /* ---- BLAS-1 style fused updates ------------------------------------------------------------------------ */
 /* MR smoother update: alpha = omega * <t,res>/<t,t> read from `dots` (as written by a stencil call with
  * in=res, out=t); phi += alpha res; res -= alpha t. */

@@ -171,6 +171,25 @@ def test_complex64_and_mixed_precision_solves():
     mg.LVL[0].apply_D(chk, xm)
     assert float(torch.linalg.vector_norm(chk - b)) < 1e-10
     assert float((xm - x64).abs().max()) < 1e-8
+    # half-precision operator storage in the preconditioner (16 coarse dof so that the half kernel is used)
+    p16 = mg2d.make_params(L, 0.0, nlevels=2, block=4, n_null=8, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-10)
+    mg16 = mg2d.setup(U, p16)
+    xa, ia = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr")
+    xh, ih = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr", precond_dtype="complex64+half")
+    assert mg16.info["single_half"].LVL[1].Dh is not None
+    assert ih["converged"] and ih["true_resnorm"] < 1e-10 and abs(ih["iters"] - ia["iters"]) <= 3
+    assert float((xh - xa).abs().max()) < 1e-8
+    # the half kernel itself against the complex64 kernel on the same data (difference = half rounding of D only)
+    l1 = mg16.info["single_half"].LVL[1]
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    ph = torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64)
+    l1.r.copy_(torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64))
+    pa, pb = ph.clone(), ph.clone()
+    l1.relax(1, phi=pa, smoother="rbgs")
+    dh, l1.Dh = l1.Dh, None
+    l1.relax(1, phi=pb, smoother="rbgs")
+    l1.Dh = dh
+    assert float((pa - pb).abs().max()) < 5e-3 * float(pb.abs().max())
     # stand-alone complex64 hierarchy: converges to single-precision accuracy
     p32 = mg2d.make_params(L, 0.0, nlevels=2, block=4, n_null=4, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-5, dtype="complex64")
     m32 = mg2d.setup(U, p32)
