@@ -37,5 +37,9 @@ def estimate_critical_mass(U, params_factory, m0: float = 0.0, iters: int = 6, r
             hist.append(lam)
             if verbose:
                 print(f"  stage {stage} m={m:+.5f} iters={info['iters']} lambda(D0)~{lam:.6f}")
-        del mg
+        mg.close()          # tens of GB at 4096^2: give them back before the next hierarchy is built
+        del mg, lv, y
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
     return -lam.real, hist

@@ -247,7 +247,7 @@ class Level:
                             lo, hi = self._halo(ph)
                             mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(rv),
                                         float(mg.p.mass), self.L, self.Ly, colour, self.y0 & 1, mg.dcode, _stream())
-                    elif self.Dh is not None and nvec == 1:
+                    elif self.Dh is not None and nvec == 1 and mg.use_half:
                         lo, hi = self._halo(phi)
                         mg.ctx.call("mg2d_relax_rb_half", _ptr(phi), lo, hi, _ptr(self.Dh), _ptr(self.D0inv_h), _ptr(r),
                                     self.n, self.L, self.Ly, colour, self.y0 & 1, _stream())
@@ -385,6 +385,7 @@ class MG:
         self.LVL = [Level(self, l) for l in range(params.nlevels + 1)]
         self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
         self.info = {}
+        self.use_half = False      # complex64 preconditioner copy: smooth with the half-precision operator blocks
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
         self.min_rows = 0
         self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
@@ -394,6 +395,18 @@ class MG:
         """Kernels of libmg2d_sm100.so launched so far (eager + replayed from graphs, minus capture-only)."""
         cap = sum(g.nlaunch for g in self.info.values() if isinstance(g, CycleGraph))
         return self.ctx.launches - cap + self.graph_launches
+
+    def close(self):
+        """Drop every device buffer and break the Level <-> MG reference cycles so that the memory returns to the
+        allocator immediately (hierarchies are tens of GB)."""
+        for lv in self.LVL + [nt for row in self.NTL for nt in row]:
+            lv.__dict__.update(phi=None, r=None, D=None, D0inv=None, Dh=None, D0inv_h=None, phi_null=None, phi_null_c=None,
+                               U=None, _work={}, mg=None)
+        for v in list(self.info.values()):
+            if isinstance(v, MG):
+                v.close()
+        self.info.clear()
+        self.LVL, self.NTL = [], []
 
     def to_device(self, a) -> torch.Tensor:
         return torch.as_tensor(np.ascontiguousarray(a)).to(self.tdtype).to(self.device)
@@ -435,7 +448,7 @@ class MG:
         lv0.compute_lvl0_matrix(U, store=True)
 
 
-def make_single_precision(mg: "MG", half_blocks: bool = False) -> "MG":
+def make_single_precision(mg: "MG") -> "MG":
     """complex64 shadow of a set-up hierarchy (links, stored operators, projectors), used as the preconditioner
     of the fp64 outer GCR: every V-cycle kernel then moves half the bytes.  The outer residual, the GCR vectors
     and the convergence test stay in complex128, so the 1e-10 TRUE residual is unaffected."""
@@ -465,8 +478,6 @@ def make_single_precision(mg: "MG", half_blocks: bool = False) -> "MG":
                 l32.U_lo_ptr = l32._U_lo.data_ptr()
             else:
                 l32.U_lo_ptr = l32.U.data_ptr() + (l32.Ly - 1) * l32.L * 2 * l32.U.element_size()
-        if half_blocks:
-            l32.make_half_blocks()
     return m32
 
 
@@ -798,9 +809,10 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         pm.ctx.call("mg2d_zero", _ptr(lv.phi), lv.S * lv.n, pm.dcode, st())
     cyc = None
     if use_graph:
-        cyc = pm.info.get("precond_graph")
+        gkey = "precond_graph_half" if pm.use_half else "precond_graph"
+        cyc = pm.info.get(gkey)
         if cyc is None:
-            cyc = pm.info["precond_graph"] = CycleGraph(pm, with_resmag=False, zero_start=True)
+            cyc = pm.info[gkey] = CycleGraph(pm, with_resmag=False, zero_start=True)
     ntl = p.ntl and p.nlevels > 0
     info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
     hist = torch.zeros(max(check_every, 1), dtype=torch.float64, device=mg.device)

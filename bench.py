@@ -234,6 +234,9 @@ def main():
         mcrit = dist_mod.bcast_float(comm, critical.estimate_critical_mass(
             U, lambda m: workload_params(mg2d, L, m), iters=4, refine=3)[0] if rank == 0 else 0.0)
     mass = mcrit + args.delta
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
     torch.cuda.synchronize()
     t_crit = time.time() - t0
     p = workload_params(mg2d, L, mass)
@@ -413,7 +416,7 @@ def main():
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic",
-        "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "plaquette": plaq, "mass": mass,
+        "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "hbm_gb_in_use": round(torch.cuda.max_memory_allocated() / 1e9, 1), "plaquette": plaq, "mass": mass,
                    "m_crit_est": mcrit, "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
                    "smoother": "rbgs V(0,4)", "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
                    "final_true_residual": info.get("true_resnorm"), "converged": info["converged"],

@@ -176,11 +176,11 @@ def test_complex64_and_mixed_precision_solves():
     mg16 = mg2d.setup(U, p16)
     xa, ia = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr")
     xh, ih = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr", precond_dtype="complex64+half")
-    assert mg16.info["single_half"].LVL[1].Dh is not None
+    assert mg16.info["single"].LVL[1].Dh is not None and mg16.info["single"].use_half
     assert ih["converged"] and ih["true_resnorm"] < 1e-10 and abs(ih["iters"] - ia["iters"]) <= 3
     assert float((xh - xa).abs().max()) < 1e-8
     # the half kernel itself against the complex64 kernel on the same data (difference = half rounding of D only)
-    l1 = mg16.info["single_half"].LVL[1]
+    l1 = mg16.info["single"].LVL[1]
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     ph = torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64)
     l1.r.copy_(torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64))
