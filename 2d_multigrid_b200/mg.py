@@ -164,7 +164,7 @@ class Level:
         """f_residue (S6/level.h:61-77): rtemp = r - D phi."""
         self._stencil(rtemp, self.phi, self.r, _lib.MODE_RESID, None)
 
-    def residue_mag_async(self, out2: torch.Tensor | None = None):
+    def residue_mag_async(self):
         """Launch the fused residual + norms of f_get_residue_mag; returns the device dots tensor
         ([0] = |r - D phi|^2, [3] = |r|^2).  No host sync."""
         d = self.dots("resmag")

@@ -83,6 +83,38 @@ def test_ntl_minres(stencil, n_copies):
     assert np.max(np.abs(ig["ntl_weights"][0][:n_copies] - io["ntl_weights"][0][:n_copies])) < 1e-8
 
 
+# config 3 at full size (2D Wilson 256x256 near-critical, non-telescoping cycle, the reference's GS smoother): the numpy
+# oracle needs minutes for this, so the GPU run is checked through size-independent properties instead
+def test_config3_wilson256_ntl_fullsize():
+    L = 256
+    th = mg2d.gauge.quenched_phases(L, 32.0, sweeps=40, device="cuda")
+    U = torch.exp(1j * th).to(torch.complex128)
+    p = mg2d.make_params(L, -0.01, nlevels=3, block=2, n_smooth=3, smoother="gs", ntl=True, n_copies=4, tol=1e-10, max_iters=400)
+    mg = mg2d.setup(U, p)                                                 # reference-compatible random start (S6/mgrid_ntl.cpp:38-48)
+    assert max(mg.info["ortho_worst"]) < 1e-12                            # f_check_ortho on every level and every NTL copy
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    lo = p.nlevels - 1
+    for q in range(4):                                                    # tests 1 and 2 of S6/tests.h for each copy / quadrant
+        nt, bot = mg.NTL[lo][q], mg.NTL[p.nlevels][q]
+        vc = torch.randn((bot.S, bot.n), generator=g, dtype=torch.float64, device="cuda").to(torch.complex128)
+        f1 = torch.zeros((nt.S, nt.n), dtype=torch.complex128, device="cuda")
+        nt.prolongation(f1, vc, q + 1)
+        c1 = torch.empty_like(vc)
+        nt.restriction(c1, f1, q + 1)
+        assert float((c1 - vc).abs().max()) < 1e-12
+        f2 = torch.empty_like(f1)
+        mg.LVL[lo].apply_D(f2, f1)
+        nt.restriction(c1, f2, q + 1)
+        c2 = torch.empty_like(vc)
+        bot.apply_D(c2, vc)
+        assert float((c1 - c2).abs().max()) < 1e-11
+    x, info = mg2d.solve(mg)
+    assert info["converged"] and info["resnorms"][-1] < 1e-10
+    assert mg.LVL[0].get_residue_mag() < 1e-10                            # true residual, recomputed
+    w = np.array(info["ntl_weights"][-1])
+    assert np.all(np.isfinite(w)) and abs(w.sum()) > 0.05                 # min-res weights are in use
+
+
 # config 4 shape at a size the oracle can follow: 8 null vectors, 4x4 aggregates
 def test_config4_shape_small():
     L = 64
