@@ -396,6 +396,20 @@ class MG:
         cap = sum(g.nlaunch for g in self.info.values() if isinstance(g, CycleGraph))
         return self.ctx.launches - cap + self.graph_launches
 
+    def _ntl_fields(self, level: int):
+        """The phi of NTL[level][0..3] live in one [4,S,n] buffer so that the Gram matrix is one batched launch."""
+        key = ("ntl_phi", level)
+        if key not in self.info:
+            lv = self.LVL[level]
+            buf = lv.new_field(4)
+            for q in range(4):
+                old = self.NTL[level][q].phi
+                if old is not None:
+                    buf[q].copy_(old)
+                self.NTL[level][q].phi = buf[q]
+            self.info[key] = buf
+        return self.info[key]
+
     def close(self):
         """Drop every device buffer and break the Level <-> MG reference cycles so that the memory returns to the
         allocator immediately (hierarchies are tens of GB)."""
@@ -622,24 +636,6 @@ def scale_phi(mg: MG, L1: Level, a, num_copies: int, lvl: int):
     E = mg._ntl_fields(lvl)
     vs = L1.S * L1.n
     mg.ctx.call("mg2d_scale_phi", _ptr(L1.phi), _ptr(E), vs, _ptr(a), num_copies, vs, mg.dcode, _stream())
-
-
-def _ntl_fields(self: MG, level: int):
-    """The phi of NTL[level][0..3] live in one [4,S,n] buffer so that the Gram matrix is one batched launch."""
-    key = ("ntl_phi", level)
-    if key not in self.info:
-        lv = self.LVL[level]
-        buf = lv.new_field(4)
-        for q in range(4):
-            old = self.NTL[level][q].phi
-            if old is not None:
-                buf[q].copy_(old)
-            self.NTL[level][q].phi = buf[q]
-        self.info[key] = buf
-    return self.info[key]
-
-
-MG._ntl_fields = _ntl_fields
 
 
 def MG_ntl(mg: MG):

@@ -1,0 +1,87 @@
+"""Drop-in interoperability with the UNMODIFIED reference program (oracle/_ref/s6_mgrid_ntl, built from /root/reference
+against oracle/eigen_shim): near-null vectors written in the reference's own file format are consumed by the reference
+(gen_null = 0, S6/modules_main.h:39-60,189) and it converges in the same number of iterations as our solver run with the
+same vectors; and the reference's own near-null file is read back and reproduces its run."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import mg2d
+from oracle import mg_oracle as O
+
+L, M, NL = 16, 0.05, 2
+
+
+def _exe(repo_root):
+    path = os.path.join(repo_root, "oracle", "_ref", "s6_mgrid_ntl")
+    if not os.path.exists(path) and os.path.isdir("/root/reference"):
+        subprocess.call(["make", "-C", os.path.join(repo_root, "oracle"), "_ref/s6_mgrid_ntl"])
+    return path if os.path.exists(path) else None
+
+
+def _run_reference(exe, theta, gen_null, nulls=None):
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "run"))
+        os.makedirs(os.path.join(d, "gauge_config_files"))
+        mg2d.gauge.write_phase_file(os.path.join(d, "gauge_config_files", f"phase_{L}_b32.0.dat"), theta, L)
+        nn = os.path.join(d, "run", mg2d.refio.near_null_filename(L, 2, 4))
+        if nulls is not None:
+            mg2d.refio.write_near_null(nn, nulls)
+        out = subprocess.run([exe, str(L), "3", "2", str(gen_null), repr(M), str(NL), "0", "1"], cwd=os.path.join(d, "run"),
+                             capture_output=True, text=True, timeout=300).stdout
+        iters = int(re.search(r"Ans (\d+)", out).group(1))
+        written = mg2d.refio.read_near_null(nn, [16, 8, 4], [2, 4, 4])
+    return iters, written
+
+
+def test_reference_consumes_our_near_null_vectors(repo_root):
+    exe = _exe(repo_root)
+    if exe is None:
+        pytest.skip("oracle/_ref/s6_mgrid_ntl not built (needs /root/reference)")
+    theta = O.gauge_quenched_phases(L, 32.0, sweeps=30, seed=77)
+    U = O.gauge_from_phases(theta)
+    p = O.Params(L=L, num_iters=3, block=2, m=M, nlevels=NL)
+    LVL, NTL, info = O.run_reference_flow(p, U)                       # our (oracle) setup + solve
+    nulls = [LVL[l].phi_null for l in range(NL)]
+    it_ref, _ = _run_reference(exe, theta, 0, nulls)                  # the reference, fed with those vectors
+    # our run from the same supplied vectors (gen_null = 0 path: norm, ortho x2, Galerkin, solve)
+    LVL2, NTL2 = O.build_reference_problem(p, U)
+    for l in range(NL):
+        LVL2[l].phi_null = nulls[l].copy()
+    O.compute_near_null(LVL2, NTL2, p, 1, gen_null=0)
+    info2 = O.perform_MG(LVL2, NTL2, p)
+    assert it_ref == info2["iters"] == info["iters"]
+
+
+def test_read_reference_near_null_file(repo_root):
+    exe = _exe(repo_root)
+    if exe is None:
+        pytest.skip("oracle/_ref/s6_mgrid_ntl not built (needs /root/reference)")
+    theta = O.gauge_quenched_phases(L, 32.0, sweeps=30, seed=78)
+    it_ref, written = _run_reference(exe, theta, 1)                   # the reference generates and writes its vectors
+    p = O.Params(L=L, num_iters=3, block=2, m=M, nlevels=NL)
+    LVL, NTL = O.build_reference_problem(p, O.gauge_from_phases(theta))
+    for l in range(NL):
+        LVL[l].phi_null = written[l].copy()
+    O.compute_near_null(LVL, NTL, p, 1, gen_null=0)
+    info = O.perform_MG(LVL, NTL, p)
+    assert info["iters"] == it_ref
+
+
+@pytest.mark.gpu
+def test_reference_consumes_gpu_near_null_vectors(repo_root):
+    """The GPU-generated near-null vectors, written in the reference format, drive the unmodified reference program to the
+    same iteration count as the GPU solve."""
+    import torch
+    exe = _exe(repo_root)
+    if exe is None:
+        pytest.skip("oracle/_ref/s6_mgrid_ntl not present on this box")
+    theta = O.gauge_quenched_phases(L, 32.0, sweeps=30, seed=79)
+    p = mg2d.make_params(L, M, nlevels=NL, block=2, n_smooth=3, smoother="gs")
+    mg, info = mg2d.run_reference_flow(p, torch.as_tensor(O.gauge_from_phases(theta)).cuda())
+    it_ref, _ = _run_reference(exe, theta, 0, [mg.LVL[l].phi_null for l in range(NL)])
+    assert info["converged"] and it_ref == info["iters"]
