@@ -12,7 +12,8 @@ HOST memory and the solution copied back to the host inside the timed region.
 Workload (config.workload): BASELINE.json configs[4]/[3] -- 2D U(1) Wilson, quenched beta=6 links generated on
 the device, mass = m_crit + 1e-3 (near-critical; m_crit located by MG inverse iteration), adaptive MG with
 8 null vectors per chirality-pair (16 coarse dof), 4x4 aggregates, levels L/4^k down to 16, red-black GS
-smoother (V(0,4) cycle: 4 post-smoothing sweeps per level, measured fastest), flexible GCR(8) outer iteration,
+smoother (no pre-smoothing; 4 / 2 / 8 / 8 ... post-smoothing sweeps on levels 0 / 1 / 2 / deeper: measured fastest),
+flexible GCR(8) outer iteration,
 complex128.
 
 Reference arm / cpu_baseline: the reference (single-threaded C++/Eigen) cannot be built for this workload --
@@ -99,8 +100,14 @@ class ClockSampler(threading.Thread):
 
 def workload_params(mg2d, L, mass, **kw):
     nlevels = max(1, int(round(math.log(L / 16, 4))))
-    return mg2d.make_params(L, mass, nlevels=nlevels, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=4, smoother="rbgs",
-                            null_iters=100, tol=TOL, max_iters=500, **kw)
+    return mg2d.make_params(L, mass, nlevels=nlevels, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=post_sweeps(nlevels),
+                            smoother="rbgs", null_iters=100, tol=TOL, max_iters=500, **kw)
+
+
+def post_sweeps(nlevels):
+    """Cycle shape measured fastest at 4096^2 (tools/tune.py): no pre-smoothing, 4 red-black sweeps on the fine lattice,
+    2 on level 1 (whose 16x16-block operator dominates the traffic of a cycle), 8 on the cheap deeper levels."""
+    return ([4, 2] + [8] * nlevels)[:nlevels + 1]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -110,15 +117,15 @@ CPU_SAMPLE_ITERS = 6      # outer iterations timed per sample (~7 s of numpy wor
 
 def oracle_setup(L_cpu: int):
     """Hierarchy of the numpy oracle on a bounded sample of the workload: same shape (block 4, 16 coarse dof,
-    rbgs V(0,4), GCR(8)), lattice L_cpu.  Not timed."""
+    rbgs post-only 4/2/8.., GCR(8)), lattice L_cpu.  Not timed."""
     import copy
     import numpy as np
     from oracle import mg_oracle as O
     nlevels = max(1, int(round(math.log(L_cpu / 16, 4))))
     th = O.gauge_quenched_phases(L_cpu, 6.0, sweeps=20, seed=1234)
     U = O.gauge_from_phases(th)
-    po = O.Params(L=L_cpu, num_iters=4, n_pre=0, n_post=4, block=4, m=-0.05, nlevels=nlevels, stencil="wilson",
-                  smoother="rbgs", n_dof_scale=16, null_iters=20)
+    po = O.Params(L=L_cpu, num_iters=4, n_pre=0, n_post=post_sweeps(nlevels), block=4, m=-0.05, nlevels=nlevels,
+                  stencil="wilson", smoother="rbgs", n_dof_scale=16, null_iters=20)
     LVL, NTL = O.build_reference_problem(po, U)
     O.compute_near_null(LVL, NTL, po, 1)
     b = np.zeros((L_cpu * L_cpu, 2), dtype=complex)
@@ -189,8 +196,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=4096)
     ap.add_argument("--delta", type=float, default=1e-3, help="mass offset above the estimated critical mass")
-    ap.add_argument("--ref-iters", type=int, default=19,
-                    help="outer iterations of the workload solve (19 measured by the GPU arm at 4096^2) used to scale the CPU sample")
+    ap.add_argument("--ref-iters", type=int, default=20,
+                    help="outer iterations of the workload solve (20 measured by the GPU arm at 4096^2) used to scale the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra solve (+ one D-apply) with cudaProfilerStart/Stop for `ncu --profile-from-start off`; "
@@ -408,7 +415,7 @@ def main():
         Lc = CPU_SAMPLE_L
         per_site_iter, it_done, t_cpu = oracle_solve(oracle_setup(Lc), CPU_SAMPLE_ITERS)
         cpu = {"value": per_site_iter * L * L * info["iters"] * 1e3, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": (f"numpy oracle port, same algorithm on a {Lc}^2 lattice (block 4, 16 coarse dof, rbgs V(0,4), GCR(8)), "
+               "sample": (f"numpy oracle port, same algorithm on a {Lc}^2 lattice (block 4, 16 coarse dof, rbgs post-only 4/2/8.., GCR(8)), "
                           f"{it_done} outer iterations in {t_cpu:.1f}s; scaled per site x iteration to {L}^2 x {info['iters']} "
                           f"iterations (extrapolated)")}
 
@@ -418,7 +425,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "hbm_gb_in_use": round(torch.cuda.max_memory_allocated() / 1e9, 1), "plaquette": plaq, "mass": mass,
                    "m_crit_est": mcrit, "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
-                   "smoother": "rbgs V(0,4)", "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
+                   "smoother": "rbgs, pre 0, post " + str(p.post), "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
                    "final_true_residual": info.get("true_resnorm"), "converged": info["converged"],
                    "setup_s": t_setup, "mcrit_s": t_crit, "cache": "working set >> L2 (126 MB); kernel timings flush L2 with a 256 MiB write",
                    "parallelism": f"strip{world}"},

@@ -124,7 +124,8 @@ def test_config4_shape_small():
     assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-8
 
 
-def test_v04_cycle_chiral_transfer_parity():
+@pytest.mark.parametrize("post", [4, [4, 2, 8]])
+def test_v04_cycle_chiral_transfer_parity(post):
     """The bench cycle shape at a size the oracle follows: V(0,4) red-black cycle inside FGCR(8), 4x4 aggregates,
     8 null vectors, chirality-compacted transfers and the overwrite-prolongation shortcut: same iteration count
     and solution as the oracle (which uses the dense projector and no shortcut)."""
@@ -132,11 +133,11 @@ def test_v04_cycle_chiral_transfer_parity():
     U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
     b = np.zeros((L * L, 2), dtype=complex)
     b[L // 2 + (L // 2) * L, 0] = 1.0
-    po = O.Params(L=L, num_iters=4, n_pre=0, n_post=4, block=4, m=-0.02, nlevels=2, null_iters=40, smoother="rbgs", n_dof_scale=16)
+    po = O.Params(L=L, num_iters=4, n_pre=0, n_post=post, block=4, m=-0.02, nlevels=2, null_iters=40, smoother="rbgs", n_dof_scale=16)
     LVLo, NTLo = O.build_reference_problem(po, U)
     O.compute_near_null(LVLo, NTLo, po, 1)
     xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=8)
-    p = mg2d.make_params(L, -0.02, nlevels=2, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=4, smoother="rbgs", null_iters=40)
+    p = mg2d.make_params(L, -0.02, nlevels=2, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=post, smoother="rbgs", null_iters=40)
     mg = mg2d.setup(T(U), p)
     assert mg.LVL[0].phi_null_c is not None and mg.LVL[0].matrix_free
     for use_graph in (False, True):

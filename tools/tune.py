@@ -29,21 +29,20 @@ def run(pre, post, mixed, restart=8):
     x, info = mg2d.solve(mg, **kw)
     torch.cuda.synchronize(); return info, (time.time() - t0) * 1e3
 configs = [
-    ("V(4,4) all", [4] * (nl + 1), [4] * (nl + 1)),
-    ("V(2,2) all", [2] * (nl + 1), [2] * (nl + 1)),
     ("V(0,4) all", [0] * (nl + 1), [4] * (nl + 1)),
-    ("V(0,6) all", [0] * (nl + 1), [6] * (nl + 1)),
-    ("V(0,8) all", [0] * (nl + 1), [8] * (nl + 1)),
-    ("V(1,3) all", [1] * (nl + 1), [3] * (nl + 1)),
-    ("l0 (4,4) l1 (2,2) rest (4,4)", [4, 2] + [4] * (nl - 1), [4, 2] + [4] * (nl - 1)),
-    ("l0 (2,2) l1 (2,2) rest (4,4)", [2, 2] + [4] * (nl - 1), [2, 2] + [4] * (nl - 1)),
-    ("l0 (0,6) l1 (0,4) rest (4,4)", [0, 0] + [4] * (nl - 1), [6, 4] + [4] * (nl - 1)),
-    ("l0 (0,4) l1 (0,3) rest (4,8)", [0, 0] + [4] * (nl - 1), [4, 3] + [8] * (nl - 1)),
-    ("l0 (0,8) l1 (0,4) rest (0,8)", [0] * (nl + 1), [8, 4] + [8] * (nl - 1)),
+    ("post [4,3,8,8,8]", [0] * (nl + 1), [4, 3] + [8] * (nl - 1)),
+    ("post [4,2,8,8,8]", [0] * (nl + 1), [4, 2] + [8] * (nl - 1)),
+    ("post [6,2,8,8,8]", [0] * (nl + 1), [6, 2] + [8] * (nl - 1)),
+    ("post [4,3,6,8,16]", [0] * (nl + 1), [4, 3, 6, 8, 16][:nl + 1]),
+    ("post [3,3,8,8,8]", [0] * (nl + 1), [3, 3] + [8] * (nl - 1)),
+    ("post [6,3,8,8,8]", [0] * (nl + 1), [6, 3] + [8] * (nl - 1)),
+    ("pre [0,0,2,2,0] post [4,3,4,4,8]", [0, 0, 2, 2, 0][:nl + 1], [4, 3, 4, 4, 8][:nl + 1]),
 ]
 for name, pre, post in configs:
     out = []
-    for mixed in (False, True):
+    for mixed in (False,):
         info, ms = run(pre, post, mixed)
         out.append(f"{'c64pc' if mixed else 'c128 '}: {info['iters']:3d} it {ms:7.1f} ms conv {info['converged']} true {info['true_resnorm']:.1e}")
+    info, ms = run(pre, post, False, restart=4)
+    out.append(f"restart4: {info['iters']:3d} it {ms:7.1f} ms")
     print(f"{name:34s} | " + " | ".join(out), flush=True)
