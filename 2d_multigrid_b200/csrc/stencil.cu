@@ -162,6 +162,75 @@ stencil_rb_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx
     }
 }
 
+// Batched red-black half sweep: NV vectors per pass share one stream of the operator blocks (near-null generation
+// relaxes nc/2 vectors with the same operator, S6/level.h:224-233; with blockIdx.y = vector the 16x16-block operator
+// would be re-streamed once per vector).  blockIdx.y selects the batch of NV vectors.
+template <typename T, int N, int NV>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_batch_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ D,
+                        const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, int Lx, int Ly, int colour, int yoff,
+                        long long vstride, long long hstride) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    constexpr int JP = G / N;
+    constexpr int ITERS = (5 * N) / JP, T0 = N / JP;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const size_t v0 = (size_t)blockIdx.y * NV;
+    phi += v0 * vstride; lo += v0 * hstride; hi += v0 * hstride;
+    if (r) r += v0 * vstride;
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    const long long nsteps = (S2 + GPB - 1) / GPB;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long h = step * GPB + grp;
+        const bool active = h < S2;
+        if (!active) h = S2 - 1;
+        const int y = (int)(h / Lh);
+        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        const size_t s = (size_t)y * Lx + x;
+        const C* Ds = D + s * 5 * N * N;
+        C acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = mk<T>(0, 0);
+#pragma unroll
+        for (int t = T0; t < ITERS; ++t) {
+            const int k = (JP * t) / N;
+            const int j = jp + (JP * t) % N;
+            const C d = __ldg(Ds + g + G * t);
+            const bool in_hi = (k == 3 && y + 1 == Ly), in_lo = (k == 4 && y == 0);
+            const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
+            const long long st = (in_hi || in_lo) ? hstride : vstride;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cfma(acc[v], d, __ldcg(p + (size_t)v * st));
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+#pragma unroll
+            for (int m = N; m < G; m <<= 1) acc[v] = cadd(acc[v], shfl_xor_c(acc[v], m));
+            if (r) acc[v] = csub(acc[v], __ldg(r + (size_t)v * vstride + s * N + i));
+        }
+        C out[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) out[v] = mk<T>(0, 0);
+        const C* Is = Dinv + s * N * N;
+#pragma unroll
+        for (int u = 0; u < N / JP; ++u) {
+            const int j = jp + JP * u;
+            const C d = __ldg(Is + j * N + i);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cfma(out[v], d, shfl_c(acc[v], j, G));
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+#pragma unroll
+            for (int m = N; m < G; m <<= 1) out[v] = cadd(out[v], shfl_xor_c(out[v], m));
+            if (active && jp == 0) phi[(size_t)v * vstride + s * N + i] = mk<T>(-out[v].x, -out[v].y);
+        }
+    }
+}
+
 // Red-black half sweep for the complex64 preconditioner hierarchy with the operator blocks stored in HALF precision
 // (`__half2` = (re,im), same [s][k][j][i] order; arithmetic and fields stay fp32).  The stored operator is the dominant
 // HBM traffic of a cycle (4 hop blocks + D0inv per updated site), so halving its bytes again is the remaining lever once the
@@ -416,6 +485,12 @@ int launch_rb(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const vo
     const long long S2 = (long long)(Lx / 2) * Ly;
     long long nsteps = (S2 + GPB - 1) / GPB;
     long long cap = (long long)ctx->num_sms * 32;
+    if (N >= 4 && nvec % 4 == 0) {     // stream the operator once per 4 vectors
+        dim3 gridb((int)(nsteps < cap ? nsteps : cap), nvec / 4);
+        stencil_rb_batch_kernel<T, N, 4><<<gridb, ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, (const C*)D, (const C*)Dinv,
+                                                                     (const C*)r, Lx, Ly, colour, yoff, vstride, hstride);
+        return mg2d_check_launch(ctx, "mg2d_relax_rb");
+    }
     dim3 grid((int)(nsteps < cap ? nsteps : cap), nvec);
     stencil_rb_kernel<T, N><<<grid, ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, (const C*)D, (const C*)Dinv,
                                                       (const C*)r, Lx, Ly, colour, yoff, vstride, hstride);

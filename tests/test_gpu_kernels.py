@@ -130,6 +130,15 @@ def test_block_stencil_all_sizes(n):
         lv.relax(2, smoother=sm)
         assert rel(lv.phi, o2.phi) < 1e-11, sm
         lv.phi.copy_(phi0)
+    # batched red-black path (4 vectors share one stream of the operator) == vector-at-a-time path
+    for nvec in (4, 8):
+        V = T(crand(rng, nvec, S, n))
+        Vb = V.clone()
+        lv.relax(2, phi=Vb, r=None, smoother="rbgs")
+        for k in range(nvec):
+            one = V[k].clone()
+            lv.relax(2, phi=one, r=None, smoother="rbgs")
+            assert float((Vb[k] - one).abs().max()) < 1e-12 * max(1.0, float(one.abs().max())), (n, nvec, k)
 
 
 def test_relax_matrix_free_and_batched():
