@@ -272,6 +272,11 @@ class Level:
         V = self.phi_null[:, :nvec, :].permute(1, 0, 2).contiguous()     # rows d1 of the random start
         vs = self.S * nf
         nrm = self.dots("nullnorm")
+        # level 0 of a matrix-free run: relax through the link field (160 B/site/sweep) instead of the stored 2x2-block
+        # operator (~400 B/site/sweep); the stored copy is only kept for the Galerkin product
+        stored = self.matrix_free
+        if self.lvl == 0 and p.matrix_free and self.U is not None:
+            self.matrix_free = True
         for _ in range(num):
             self.relax(p.null_chunk, phi=V, r=None)
             for v in range(nvec):
@@ -279,6 +284,7 @@ class Level:
             self.allreduce(nrm[:nvec])
             for v in range(nvec):
                 mg.ctx.call("mg2d_scale_inv_norm", _ptr(V[v]), _ptr(nrm[v:]), vs, mg.dcode, _stream())
+        self.matrix_free = stored
         mg.ctx.call("mg2d_pack_null", _ptr(self.phi_null), _ptr(V), nvec, vs, nf, nc, self.S, int(wilson),
                     mg.dcode, _stream())
 
