@@ -38,6 +38,10 @@ CASES = [
     ("s6_laplace16_2lvl", "laplace", 16, 3, 2, 0.05, 2, 0, 1, 30),
     ("s6_laplace16_ntl4", "laplace", 16, 3, 2, 0.05, 2, 1, 4, 30),
     ("s6_wilson16_relax_only", "wilson", 16, 10, 2, 0.3, 0, 0, 1, 30),
+    ("s6_wilson16_blk4", "wilson", 16, 3, 4, 0.05, 1, 0, 1, 30),
+    ("s6_wilson16_ntl3", "wilson", 16, 3, 2, 0.05, 2, 1, 3, 30),
+    ("s6_wilson32_negmass_2lvl", "wilson", 32, 4, 2, -0.01, 2, 0, 1, 50),
+    ("s6_laplace16_blk4", "laplace", 16, 3, 4, 0.1, 1, 0, 1, 30),
 ]
 
 
