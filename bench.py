@@ -110,8 +110,8 @@ def post_sweeps(nlevels):
 
 
 # ---------------------------------------------------------------------------------------------------------
-CPU_SAMPLE_L = 256        # lattice of the bounded CPU sample (same hierarchy shape as the workload)
-CPU_SAMPLE_ITERS = 6      # outer iterations timed per sample (~7 s of numpy work)
+CPU_SAMPLE_L = int(os.environ.get("MG2D_CPU_SAMPLE_L", "256"))   # lattice of the bounded CPU sample (workload's hierarchy shape)
+CPU_SAMPLE_ITERS = 6      # outer iterations timed per sample (~7 s of numpy work at 256^2)
 
 
 def oracle_setup(L_cpu: int):
