@@ -84,3 +84,23 @@ def test_phase_file_roundtrip(tmp_path):
     lines = open(f).read().split()
     # x outer, y inner, dir inner (S6/gauge.h:103-107): second record is (x=0,y=0,dir=1), third (x=0,y=1,dir=0)
     assert abs(float(lines[1]) - th[0, 1]) < 1e-15 and abs(float(lines[2]) - th[L, 0]) < 1e-15
+
+
+def test_error_spectrum_diagnostics():
+    """A single plane wave error shows up in exactly one FFT bin (NB/2_spectral_analysis_solution.ipynb cell 5)."""
+    import numpy as np
+    import torch
+    L, kx, ky = 16, 3, 5
+    s = np.arange(L * L)
+    x, y = s % L, s // L
+    err = np.exp(2j * np.pi * (kx * x + ky * y) / L)
+    phi_star = torch.zeros((L * L, 2), dtype=torch.complex128)
+    phi = phi_star.clone()
+    phi[:, 1] = torch.as_tensor(err)
+    spec = mg2d.diagnostics.error_spectrum(phi, phi_star, L)
+    assert spec.shape == (2, L, L)
+    assert abs(float(spec[1, ky, kx]) - L * L) < 1e-9 and float(spec[0].max()) == 0.0
+    spec[1, ky, kx] = 0
+    assert float(spec.max()) < 1e-9
+    lo, hi = mg2d.diagnostics.mode_amplitudes(phi, phi_star, L)
+    assert hi > 100 and lo < 1e-9        # (3,5): ky > L/4 -> a high-frequency mode
