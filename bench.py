@@ -402,7 +402,8 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_L{L}.json")
     if os.path.exists(traffic_file):
         try:
-            traffic = json.load(open(traffic_file)).get(dom["kernel"].split(" ")[0])
+            tj = {k.replace(" ", ""): v for k, v in json.load(open(traffic_file)).items() if isinstance(v, (int, float))}
+            traffic = tj.get(dom["kernel"].split(" ")[0].replace(" ", ""))
             if traffic is not None and " x2 " in dom["kernel"]:
                 traffic *= 2          # the timed unit is a full sweep = two half-sweep launches
         except Exception:
