@@ -169,6 +169,52 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def reference_binary_config2(mg2d=None):
+    """BASELINE configs[1] (2D U(1) Wilson 64x64, adaptive 3-level MG, the reference's Gauss-Seidel smoother, fp64) run by
+    the reference's OWN program -- the unmodified S6 source compiled against oracle/eigen_shim (oracle/_ref/s6_mgrid_ntl),
+    wall time of the whole process (setup, 500-sweep near-null generation, solve, its per-iteration text output) -- and by
+    this package on the same links with the same algorithm (exact lexicographic GS, stationary cycle, tol 1e-13).
+    Returns None when the binary is not present."""
+    import re
+    import subprocess
+    import tempfile
+    import numpy as np
+    from oracle import mg_oracle as O
+    exe = os.path.join(ROOT, "oracle", "_ref", "s6_mgrid_ntl")
+    if not os.path.exists(exe):
+        return None
+    L, m, nl = 64, -0.01, 2
+    theta = O.gauge_quenched_phases(L, 32.0, sweeps=30, seed=1234)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "run"))
+        os.makedirs(os.path.join(d, "gauge_config_files"))
+        O.write_phase_file(os.path.join(d, "gauge_config_files", f"phase_{L}_b32.0.dat"), theta, L)
+        t0 = time.perf_counter()
+        out = subprocess.run([exe, str(L), "3", "2", "1", repr(m), str(nl), "0", "1"], cwd=os.path.join(d, "run"),
+                             capture_output=True, text=True, timeout=900).stdout
+        t_ref = time.perf_counter() - t0
+    it_ref = int(re.search(r"Ans (\d+)", out).group(1))
+    res = {"config": "wilson64_adaptive_3level_gs (BASELINE configs[1]): L=64 m=-0.01 beta=32 block 2, 3 GS sweeps, tol 1e-13",
+           "reference_binary_s": t_ref, "reference_iters": it_ref, "cores": 1,
+           "note": "reference = unmodified S6 source + oracle/eigen_shim (Eigen absent); wall time of the whole program"}
+    if mg2d is not None:
+        import torch
+        U = torch.as_tensor(O.gauge_from_phases(theta)).cuda()
+        p = mg2d.make_params(L, m, nlevels=nl, block=2, n_smooth=3, smoother="gs")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mg = mg2d.setup(U, p, init="reference")
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        x, info = mg2d.solve(mg)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        res.update({"gpu_setup_s": t1 - t0, "gpu_solve_s": t2 - t1, "gpu_iters": info["iters"],
+                    "gpu_final_residual": info["resnorms"][-1], "iters_identical": info["iters"] == it_ref})
+        mg.close()
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------
 def time_kernel(fn, reps, flush=None):
     import torch
@@ -419,6 +465,13 @@ def main():
                           f"{it_done} outer iterations in {t_cpu:.1f}s; scaled per site x iteration to {L}^2 x {info['iters']} "
                           f"iterations (extrapolated)")}
 
+    config2 = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            config2 = reference_binary_config2(mg2d)
+        except Exception as e:      # an extra, never allowed to break the bench line
+            config2 = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
@@ -442,6 +495,7 @@ def main():
                                  "note": "as mixed_precision, with the coarse operators of the complex64 copy stored as __half2 (fp32 arithmetic)"},
         "kernels": table,
         "cpu_baseline": cpu,
+        "config2_vs_reference_binary": config2,
     }
     print(json.dumps(line), flush=True)
     _finish(comm)
