@@ -144,3 +144,30 @@ def test_gcr_and_smoothers_agree_on_solution():
         xs.append(x)
     for x in xs[1:]:
         assert np.max(np.abs(x - xs[0])) < 1e-9
+
+
+def test_c_port_matches_numpy_oracle():
+    """oracle/c_port (plain C + OpenMP restatement of the solve loop, used as the CPU baseline of bench.py) against the
+    numpy oracle on the bench's cycle shape: same iteration count, residual history and solution."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from oracle import c_port
+    L = 32
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=20))
+    p = O.Params(L=L, num_iters=4, n_pre=0, n_post=[4, 2], block=4, m=-0.02, nlevels=1, smoother="rbgs", n_dof_scale=16, null_iters=20)
+    LVL, NTL = O.build_reference_problem(p, U)
+    O.compute_near_null(LVL, NTL, p, 1)
+    b = np.zeros((L * L, 2), dtype=complex)
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    import copy
+    xo, io = O.gcr_MG(copy.deepcopy(LVL), NTL, p, b, tol=1e-10, restart=8)
+    xc, ic = c_port.gcr_solve(LVL, p, b, tol=1e-10, restart=8)
+    assert ic["iters"] == io["iters"] and ic["converged"]
+    assert max(abs(a / c - 1) for a, c in zip(ic["resnorms"], io["resnorms"])) < 1e-8
+    assert np.max(np.abs(xc - xo)) < 1e-12 * np.max(np.abs(xo))
+    # pre-smoothing path too
+    p2 = O.Params(L=L, num_iters=2, block=4, m=-0.02, nlevels=1, smoother="rbgs", n_dof_scale=16, null_iters=20)
+    xo2, io2 = O.gcr_MG(copy.deepcopy(LVL), NTL, p2, b, tol=1e-10, restart=4)
+    xc2, ic2 = c_port.gcr_solve(LVL, p2, b, tol=1e-10, restart=4)
+    assert ic2["iters"] == io2["iters"] and np.max(np.abs(xc2 - xo2)) < 1e-12 * np.max(np.abs(xo2))
