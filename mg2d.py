@@ -5,3 +5,8 @@ import sys
 
 _pkg = importlib.import_module("2d_multigrid_b200")
 sys.modules[__name__] = _pkg
+
+
+if __name__ == "__main__":          # `python mg2d.py ...` == `python -m 2d_multigrid_b200 ...`
+    import runpy
+    runpy.run_module("2d_multigrid_b200", run_name="__main__")

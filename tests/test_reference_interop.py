@@ -85,3 +85,28 @@ def test_reference_consumes_gpu_near_null_vectors(repo_root):
     mg, info = mg2d.run_reference_flow(p, torch.as_tensor(O.gauge_from_phases(theta)).cuda())
     it_ref, _ = _run_reference(exe, theta, 0, [mg.LVL[l].phi_null for l in range(NL)])
     assert info["converged"] and it_ref == info["iters"]
+
+
+@pytest.mark.gpu
+def test_cli_drop_in(repo_root):
+    """`python mg2d.py L num_iters block gen_null m nlevels t_flag n_copies` in a directory laid out like the reference's
+    (../gauge_config_files/phase_L_b32.0.dat) prints the same "Ans" as the reference program and writes the same files."""
+    import sys
+    exe = _exe(repo_root)
+    theta = O.gauge_quenched_phases(L, 32.0, sweeps=30, seed=80)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "run"))
+        os.makedirs(os.path.join(d, "gauge_config_files"))
+        mg2d.gauge.write_phase_file(os.path.join(d, "gauge_config_files", f"phase_{L}_b32.0.dat"), theta, L)
+        argv = [str(L), "3", "2", "1", repr(M), str(NL), "0", "1"]
+        out = subprocess.run([sys.executable, os.path.join(repo_root, "mg2d.py")] + argv, cwd=os.path.join(d, "run"),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-1500:]
+        ans = int(re.search(r"Ans (\d+)", out.stdout).group(1))
+        assert os.path.exists(os.path.join(d, "run", "results_phi.txt"))
+        assert os.path.exists(os.path.join(d, "run", mg2d.refio.near_null_filename(L, 2, 4)))
+        row = open(os.path.join(d, "run", "results_gen_scaling.txt")).read().split()
+        assert int(row[-1]) == ans and int(row[0]) == L
+        if exe is not None:
+            ref = subprocess.run([exe] + argv, cwd=os.path.join(d, "run"), capture_output=True, text=True, timeout=300).stdout
+            assert int(re.search(r"Ans (\d+)", ref).group(1)) == ans
