@@ -15,7 +15,7 @@ C128, C64 = 0, 1
 MODE_APPLY, MODE_RESID = 0, 1
 DOT_OUT2, DOT_OUTIN_RE, DOT_OUTIN_IM, DOT_B2, NDOTS = 0, 1, 2, 3, 4
 
-_vp, _i, _d, _ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+_vp, _i, _d, _ll, _ull = C.c_void_p, C.c_int, C.c_double, C.c_longlong, C.c_ulonglong
 
 # name -> argtypes (after the leading mg2d_ctx*); mirrors include/mg2d.h one to one
 SIGNATURES = {
@@ -27,6 +27,9 @@ SIGNATURES = {
     "mg2d_relax_gs": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp],
     "mg2d_relax_rb": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
     "mg2d_wilson_relax_rb": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _i, _vp],
+    "mg2d_wilson_relax_rb2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp],
+    "mg2d_premultiply": [_vp, _vp, _vp, _i, _ll, _i, _vp],
+    "mg2d_relax_rb_pm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
     "mg2d_relax_rb_half": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mg2d_to_half": [_vp, _vp, _ll, _vp],
     "mg2d_axpy_ratio2": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _i, _vp],
@@ -55,6 +58,10 @@ SIGNATURES = {
     "mg2d_ipc_alloc": [_ll, C.POINTER(_vp), _vp],
     "mg2d_ipc_open": [_vp, C.POINTER(_vp)],
     "mg2d_halo_exchange": [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mg2d_fill_uniform": [_vp, _ll, _ll, _ull, _ull, _d, _d, _i, _vp],
+    "mg2d_gauge_metropolis": [_vp, _i, _d, _d, _i, _i, _ull, _ull, _vp],
+    "mg2d_plaquette": [_vp, _i, _i, _vp, _vp],
+    "mg2d_phases_to_links": [_vp, _vp, _ll, _i, _vp],
     "mg2d_s2_relax": [_vp, _vp, _i, _d, _d, _i, _i, _vp],
     "mg2d_s2_project": [_vp, _vp, _vp, _i, _d, _d, _i, _vp],
     "mg2d_s2_interpolate": [_vp, _vp, _i, _i, _vp],

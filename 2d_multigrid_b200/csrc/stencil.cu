@@ -231,6 +231,94 @@ stencil_rb_batch_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, cons
     }
 }
 
+// Red-black half sweep on PRE-MULTIPLIED hopping blocks  M_k(s) = -D0(s)^-1 D_k(s), k = 1..4  (layout M[s][k-1][j][i]):
+//     phi(s) <- sum_k M_k(s) phi(s+d_k) + c(s),   c(s) = D0(s)^-1 r(s)
+// which is f_relax's update (S6/level.h:116-121) with the inverse folded into the blocks: 4 n x n blocks per updated
+// site instead of 5 (the level-1 sweep of the bench sits at the HBM roofline, so only fewer bytes make it faster),
+// and no second dependent mat-vec phase (shorter critical path on the small, latency-bound levels).
+// CMODE 0: r = 0 (near-null relaxation); 1: first sweep of a relax call, c = D0^-1 r is computed here and stored in
+// cbuf; 2: c read from cbuf.  NV vectors per pass share one stream of the blocks (blockIdx.y = batch of NV).
+template <typename T, int N, int NV, int CMODE>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ M,
+                     const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, cplx<T>* cbuf, int Lx, int Ly,
+                     int colour, int yoff, long long vstride, long long hstride) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    constexpr int JP = G / N;
+    constexpr int ITERS = (4 * N) / JP;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const size_t v0 = (size_t)blockIdx.y * NV;
+    phi += v0 * vstride; lo += v0 * hstride; hi += v0 * hstride;
+    if (CMODE == 1) r += v0 * vstride;
+    if (CMODE != 0) cbuf += v0 * vstride;
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    const long long nsteps = (S2 + GPB - 1) / GPB;
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long h = step * GPB + grp;
+        const bool active = h < S2;
+        if (!active) h = S2 - 1;
+        const int y = (int)(h / Lh);
+        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        const size_t s = (size_t)y * Lx + x;
+        const C* Ms = M + s * 4 * N * N;
+        C acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = mk<T>(0, 0);
+#pragma unroll
+        for (int t = 0; t < ITERS; ++t) {
+            const int k = 1 + (JP * t) / N;
+            const int j = jp + (JP * t) % N;
+            const C d = __ldg(Ms + g + G * t);
+            const bool in_hi = (k == 3 && y + 1 == Ly), in_lo = (k == 4 && y == 0);
+            const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
+            const long long st = (in_hi || in_lo) ? hstride : vstride;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) cfma(acc[v], d, __ldcg(p + (size_t)v * st));
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+#pragma unroll
+            for (int m = N; m < G; m <<= 1) acc[v] = cadd(acc[v], shfl_xor_c(acc[v], m));
+            if (CMODE == 1) {
+                const C w = __ldg(r + (size_t)v * vstride + s * N + i);
+                const C c = apply_minus_inv<T, N, G>(Dinv + s * N * N, w, g);       // = -D0^-1 r
+                acc[v] = csub(acc[v], c);
+                if (active && jp == 0) cbuf[(size_t)v * vstride + s * N + i] = mk<T>(-c.x, -c.y);
+            } else if (CMODE == 2) {
+                acc[v] = cadd(acc[v], __ldg(cbuf + (size_t)v * vstride + s * N + i));
+            }
+            if (active && jp == 0) phi[(size_t)v * vstride + s * N + i] = acc[v];
+        }
+    }
+}
+
+// M[s][k-1] = -D0inv[s] D[s][k], k = 1..4 (column-major blocks).  One CTA walks over sites; the site's D0^-1 and
+// the four hopping blocks are staged in shared memory.
+template <typename T, int N>
+__global__ void __launch_bounds__(256)
+premultiply_kernel(cplx<T>* __restrict__ M, const cplx<T>* __restrict__ D, const cplx<T>* __restrict__ Dinv, long long S) {
+    using C = cplx<T>;
+    __shared__ C s_inv[N * N];
+    __shared__ C s_d[4 * N * N];
+    for (long long s = blockIdx.x; s < S; s += gridDim.x) {
+        for (int e = threadIdx.x; e < N * N; e += blockDim.x) s_inv[e] = __ldg(Dinv + (size_t)s * N * N + e);
+        for (int e = threadIdx.x; e < 4 * N * N; e += blockDim.x) s_d[e] = __ldg(D + (size_t)s * 5 * N * N + N * N + e);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 4 * N * N; e += blockDim.x) {
+            const int k = e / (N * N), j = (e / N) % N, i = e % N;
+            C a = mk<T>(0, 0);
+#pragma unroll 4
+            for (int l = 0; l < N; ++l) cfma(a, s_inv[l * N + i], s_d[k * N * N + j * N + l]);
+            M[(size_t)s * 4 * N * N + e] = mk<T>(-a.x, -a.y);
+        }
+        __syncthreads();
+    }
+}
+
 // Red-black half sweep for the complex64 preconditioner hierarchy with the operator blocks stored in HALF precision
 // (`__half2` = (re,im), same [s][k][j][i] order; arithmetic and fields stay fp32).  The stored operator is the dominant
 // HBM traffic of a cycle (4 hop blocks + D0inv per updated site), so halving its bytes again is the remaining lever once the
@@ -510,6 +598,49 @@ int dispatch_rb(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* hi,
 }
 
 template <typename T, int N>
+int launch_rb_pm(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* M, const void* Dinv, const void* r,
+                 void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride, long long hstride,
+                 cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    const long long S2 = (long long)(Lx / 2) * Ly;
+    long long nsteps = (S2 + GPB - 1) / GPB;
+    long long cap = (long long)ctx->num_sms * 32;
+    const int gx = (int)(nsteps < cap ? nsteps : cap);
+#define PM(NV, CM) stencil_rb_pm_kernel<T, N, NV, CM><<<dim3(gx, nvec / NV), ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
+        (const C*)M, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, vstride, hstride)
+    if (N >= 4 && nvec % 4 == 0) { if (cmode == 0) PM(4, 0); else if (cmode == 1) PM(4, 1); else PM(4, 2); }
+    else                         { if (cmode == 0) PM(1, 0); else if (cmode == 1) PM(1, 1); else PM(1, 2); }
+#undef PM
+    return mg2d_check_launch(ctx, "mg2d_relax_rb_pm");
+}
+
+template <typename T>
+int dispatch_rb_pm(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* hi, const void* M, const void* Dinv,
+                   const void* r, void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride,
+                   long long hstride, cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_rb_pm<T, N>(ctx, phi, lo, hi, M, Dinv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb_pm: n_dof must be one of 1,2,4,8,16,32");
+    }
+}
+
+template <typename T>
+int dispatch_premul(mg2d_ctx* ctx, int n, void* M, const void* D, const void* Dinv, long long S, cudaStream_t st) {
+    using C = cplx<T>;
+    long long nb = S; if (nb > (long long)ctx->num_sms * 16) nb = (long long)ctx->num_sms * 16;
+    switch (n) {
+#define CASE(N) case N: premultiply_kernel<T, N><<<(int)nb, 256, 0, st>>>((C*)M, (const C*)D, (const C*)Dinv, S); break
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_premultiply: n_dof must be one of 1,2,4,8,16");
+    }
+    return mg2d_check_launch(ctx, "mg2d_premultiply");
+}
+
+template <typename T, int N>
 int launch_inverse(mg2d_ctx* ctx, void* Dinv, const void* D, long long S, cudaStream_t st) {
     using C = cplx<T>;
     const size_t per_warp = 2 * (size_t)N * N * sizeof(C);
@@ -618,4 +749,26 @@ extern "C" int mg2d_relax_rb_half(mg2d_ctx* ctx, void* phi, const void* phi_lo, 
     }
 #undef RBH
     return mg2d_check_launch(ctx, "mg2d_relax_rb_half");
+}
+
+extern "C" int mg2d_premultiply(mg2d_ctx* ctx, void* M, const void* D, const void* D0inv, int n, long long nsites, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!M || !D || !D0inv || nsites < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_premultiply: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_premul<double>(ctx, n, M, D, D0inv, nsites, st);
+    if (dtype == MG2D_C64)  return dispatch_premul<float>(ctx, n, M, D, D0inv, nsites, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_premultiply: bad dtype");
+}
+
+extern "C" int mg2d_relax_rb_pm(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* M, const void* D0inv,
+                                const void* r, void* cbuf, int cmode, int n, int Lx, int Ly, int colour, int yoff, int dtype,
+                                int nvec, long long vstride, long long hstride, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !M || Lx < 2 || (Lx & 1) || Ly < 1 || nvec < 1 || (colour != 0 && colour != 1) ||
+        cmode < 0 || cmode > 2 || (cmode == 1 && (!r || !D0inv || !cbuf)) || (cmode == 2 && !cbuf))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm: bad argument (Lx must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_rb_pm<double>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
+    if (dtype == MG2D_C64)  return dispatch_rb_pm<float>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm: bad dtype");
 }

@@ -84,11 +84,11 @@ class Comm:
         dist.barrier(group=self.group)
         self.p2p = {"ctx": ctx, "base": base, "slots": 0, "off": SLOT_REGION, "size": slab_bytes, "keys": {}}
 
-    def _p2p_exchange(self, t, Lx, Ly, width, nvec, key):
+    def _p2p_exchange(self, t, Lx, Ly, width, nvec, key, depth=1):
         from .mg import _stream
         st = self.p2p
         es = t.element_size()
-        row = Lx * width * es
+        row = Lx * width * es * depth         # `depth` boundary rows are one contiguous piece
         k = (key, nvec, row)
         if k not in st["keys"]:
             need = ((nvec * row + 255) // 256) * 256
@@ -101,7 +101,7 @@ class Comm:
         b = st["base"]
         me, pv, nx = b[self.rank], b[self.prev], b[self.next]
         stride = Ly * Lx * width * es
-        st["ctx"].call("mg2d_halo_exchange", t.data_ptr(), t.data_ptr() + (Ly - 1) * row, stride, row, nvec,
+        st["ctx"].call("mg2d_halo_exchange", t.data_ptr(), t.data_ptr() + stride - row, stride, row, nvec,
                        nx + lo_off, pv + hi_off, me + slot, pv + slot, nx + slot, _stream())
         return _Ptr(me + lo_off), _Ptr(me + hi_off)
 
@@ -119,15 +119,16 @@ class Comm:
         cudart.cudaMemcpy(buf, C.c_void_p(self.p2p["base"][self.rank]), C.c_size_t(64 * n), C.c_int(2))
         return int(sum(buf[8 * i + 5] for i in range(n)))
 
-    def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None, as_tensor: bool = False):
-        """Returns (lo, hi): the row below local row 0 (last row of rank-1) and the row above the last local row
-        (first row of rank+1), periodic.  t: [Ly*Lx, width...] or a batch [nvec, Ly*Lx, width]."""
+    def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None, as_tensor: bool = False,
+                      depth: int = 1):
+        """Returns (lo, hi): the `depth` rows below local row 0 (last rows of rank-1) and above the last local row
+        (first rows of rank+1), periodic.  t: [Ly*Lx, width...] or a batch [nvec, Ly*Lx, width]."""
         if self.p2p is not None and not as_tensor and t.is_cuda and (Lx * width * t.element_size()) % 16 == 0:
-            return self._p2p_exchange(t, Lx, Ly, width, nvec, key)
+            return self._p2p_exchange(t, Lx, Ly, width, nvec, key, depth)
         if nvec == 1:
-            first, last = t[:Lx], t[(Ly - 1) * Lx:Ly * Lx]
+            first, last = t[:depth * Lx], t[(Ly - depth) * Lx:Ly * Lx]
         else:
-            first, last = t[:, :Lx].contiguous(), t[:, (Ly - 1) * Lx:Ly * Lx].contiguous()
+            first, last = t[:, :depth * Lx].contiguous(), t[:, (Ly - depth) * Lx:Ly * Lx].contiguous()
         k = (key, tuple(first.shape), first.dtype)
         if k not in self._halo:
             self._halo[k] = (torch.empty_like(first), torch.empty_like(first))

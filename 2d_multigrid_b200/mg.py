@@ -58,6 +58,7 @@ class Level:
         self.r = None
         self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
         self.D0inv = None
+        self.M = None          # [S,4,n,n]: pre-multiplied hopping blocks -D0^-1 D_k of the red-black smoother
         self.Dh = None         # optional half-precision copies (__half2) of D / D0inv for the complex64 preconditioner
         self.D0inv_h = None
         self.phi_null = None   # [S,nc,nf]
@@ -87,17 +88,18 @@ class Level:
         self.y0, self.Ly, self.distributed = y0, Ly, True
         self.S = self.L * Ly
 
-    def _halo(self, t: torch.Tensor, nvec: int = 1, width: int | None = None):
-        """(lo, hi) row pointers for a field [S, width] (or a batch [nvec, S, width]) of this level: the periodic
-        wrap rows on one GPU, the exchanged neighbour rows (NCCL send/recv) on a strip."""
+    def _halo(self, t: torch.Tensor, nvec: int = 1, width: int | None = None, depth: int = 1):
+        """(lo, hi) pointers to the `depth` rows below local row 0 (rows -depth..-1) and above the last local row
+        (rows Ly..Ly+depth-1) of a field [S, width] (or a batch [nvec, S, width]) of this level: the periodic wrap
+        rows on one GPU, the exchanged neighbour rows on a strip."""
         width = self.n if width is None else width
         if self.distributed:
-            lo, hi = self.mg.comm.exchange_rows(t, self.L, self.Ly, width, nvec, key=(self.lvl, width, nvec))
+            lo, hi = self.mg.comm.exchange_rows(t, self.L, self.Ly, width, nvec, key=(self.lvl, width, nvec, depth), depth=depth)
             return lo.data_ptr(), hi.data_ptr()
         t0 = t if nvec == 1 else t[0]
         es = t0.element_size() * width
         base = t0.data_ptr()
-        return base + (self.Ly - 1) * self.L * es, base
+        return base + (self.Ly - depth) * self.L * es, base
 
     def allreduce(self, t, op: str = "sum"):
         if self.distributed:
@@ -123,18 +125,31 @@ class Level:
         mg, p = self.mg, self.mg.p
         assert self.lvl == 0
         self.U = U
-        if self.distributed:   # link row below the strip: exchanged once
-            lo, _hi = mg.comm.exchange_rows(U, self.L, self.Ly, 2, 1, key=("U",), as_tensor=True)
-            self._U_lo = lo.clone()
-            self.U_lo_ptr = self._U_lo.data_ptr()
-        else:
-            self.U_lo_ptr = U.data_ptr() + (self.Ly - 1) * self.L * 2 * U.element_size()
+        self.bind_link_halos(None)
         if store:
             self.D = torch.empty((self.S, 5, self.n, self.n), dtype=mg.tdtype, device=mg.device)
             mg.ctx.call("mg2d_lvl0_matrix", _ptr(self.D), _ptr(U), self.U_lo_ptr, float(p.mass),
                         0 if p.stencil == "wilson" else 1, self.L, self.Ly, mg.dcode, _stream())
             self.D0inv = None
+            self.M = None
         self.matrix_free = not store
+
+    def bind_link_halos(self, halos):
+        """Link rows outside the strip: two below (U_lo2: rows -2, -1; the two-colour smoother recomputes one row of
+        the neighbour's red sites) and one above (U_hi).  Exchanged once per gauge field (halos None) or taken from
+        `halos` = (lo2, hi) tensors (precision copies); on one GPU they are the periodic wrap rows of U itself."""
+        U = self.U
+        row = self.L * 2 * U.element_size()
+        if self.distributed:
+            if halos is None:
+                lo2, hi2 = self.mg.comm.exchange_rows(U, self.L, self.Ly, 2, 1, key=("U",), as_tensor=True, depth=2)
+                halos = (lo2.clone(), hi2[:self.L].clone())
+            self._U_halos = halos
+            self.U_lo2_ptr, self.U_hi_ptr = halos[0].data_ptr(), halos[1].data_ptr()
+        else:
+            self._U_halos = None
+            self.U_lo2_ptr, self.U_hi_ptr = U.data_ptr() + (self.Ly - 2) * row, U.data_ptr()
+        self.U_lo_ptr = self.U_lo2_ptr + row          # row -1
 
     def _stencil(self, out, vin, b, mode, dots, nvec=1):
         mg = self.mg
@@ -196,6 +211,13 @@ class Level:
             self.D0inv = torch.empty((self.S, self.n, self.n), dtype=self.mg.tdtype, device=self.mg.device)
             self.mg.ctx.call("mg2d_block_inverse", _ptr(self.D0inv), _ptr(self.D), self.n, self.S, self.mg.dcode, _stream())
 
+    def _ensure_M(self):
+        """M[s][k-1] = -D0(s)^-1 D_k(s): the hopping blocks with f_relax's inverse (S6/level.h:116) folded in."""
+        if self.M is None:
+            self._ensure_D0inv()
+            self.M = torch.empty((self.S, 4, self.n, self.n), dtype=self.mg.tdtype, device=self.mg.device)
+            self.mg.ctx.call("mg2d_premultiply", _ptr(self.M), _ptr(self.D), _ptr(self.D0inv), self.n, self.S, self.mg.dcode, _stream())
+
     def relax(self, num_iter: int, gs_flag: int | None = None, phi=None, r="self", smoother: str | None = None):
         """f_relax (S6/level.h:100-128).  gs_flag 1 = lexicographic Gauss-Seidel, 0 = Jacobi (reference);
         smoother='mr' = minimal residual (north_star).  phi may be a batch [nvec, S, n]; r=None means r=0."""
@@ -236,9 +258,24 @@ class Level:
                 self.allreduce(d[:4 * nvec])
                 mg.ctx.call("mg2d_mr_update", _ptr(phi), _ptr(res), _ptr(t), _ptr(d), float(mg.p.mr_omega),
                             vs, mg.dcode, nvec, vs, _stream())
+        elif smoother == "rbgs" and self.matrix_free and mg.two_colour and self.Ly >= 2:
+            # both colours per pass, out of place (mg2d_wilson_relax_rb2): ping-pong between phi and a work buffer
+            tmp = self.work("rb2_tmp", None if nvec == 1 else nvec)
+            for v in range(nvec):
+                cur, nxt = (phi, tmp) if nvec == 1 else (phi[v], tmp[v])
+                rv = None if r is None else (r if nvec == 1 else r[v])
+                r_lo, r_hi = (None, None) if rv is None else self._halo(rv)
+                for _ in range(num_iter):
+                    lo2, hi2 = self._halo(cur, depth=2)
+                    mg.ctx.call("mg2d_wilson_relax_rb2", _ptr(nxt), _ptr(cur), lo2, hi2, _ptr(self.U), self.U_lo2_ptr,
+                                self.U_hi_ptr, _ptr(rv), r_lo, r_hi, float(mg.p.mass), self.L, self.Ly, self.y0 & 1,
+                                mg.dcode, _stream())
+                    cur, nxt = nxt, cur
+                if num_iter & 1:
+                    mg.ctx.call("mg2d_copy", _ptr(nxt), _ptr(cur), vs, mg.dcode, _stream())
         elif smoother == "rbgs":
             hs = self.L * self.n if (self.distributed and nvec > 1) else vs
-            for _ in range(num_iter):
+            for it in range(num_iter):
                 for colour in (0, 1):
                     if self.matrix_free:
                         for v in range(nvec):
@@ -251,6 +288,14 @@ class Level:
                         lo, hi = self._halo(phi)
                         mg.ctx.call("mg2d_relax_rb_half", _ptr(phi), lo, hi, _ptr(self.Dh), _ptr(self.D0inv_h), _ptr(r),
                                     self.n, self.L, self.Ly, colour, self.y0 & 1, _stream())
+                    elif mg.premul and self.n <= 16:
+                        # pre-multiplied blocks M_k = -D0^-1 D_k: 4 blocks per updated site instead of 5
+                        self._ensure_M()
+                        cmode = 0 if r is None else (1 if it == 0 else 2)
+                        cbuf = None if r is None else self.work("pm_c", None if nvec == 1 else nvec)
+                        lo, hi = self._halo(phi, nvec)
+                        mg.ctx.call("mg2d_relax_rb_pm", _ptr(phi), lo, hi, _ptr(self.M), _ptr(self.D0inv), _ptr(r), _ptr(cbuf),
+                                    cmode, self.n, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, nvec, vs, hs, _stream())
                     else:
                         self._ensure_D0inv()
                         lo, hi = self._halo(phi, nvec)
@@ -392,6 +437,8 @@ class MG:
         self.NTL = [[Level(self, l) for _ in range(4)] for l in range(params.nlevels + 1)]
         self.info = {}
         self.use_half = False      # complex64 preconditioner copy: smooth with the half-precision operator blocks
+        self.premul = True         # red-black sweeps on stored operators use the pre-multiplied blocks -D0^-1 D_k
+        self.two_colour = True     # level-0 matrix-free red-black sweeps through the one-pass two-colour kernel
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
         self.min_rows = 0
         self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
@@ -420,8 +467,8 @@ class MG:
         """Drop every device buffer and break the Level <-> MG reference cycles so that the memory returns to the
         allocator immediately (hierarchies are tens of GB)."""
         for lv in self.LVL + [nt for row in self.NTL for nt in row]:
-            lv.__dict__.update(phi=None, r=None, D=None, D0inv=None, Dh=None, D0inv_h=None, phi_null=None, phi_null_c=None,
-                               U=None, _work={}, mg=None)
+            lv.__dict__.update(phi=None, r=None, D=None, D0inv=None, M=None, Dh=None, D0inv_h=None, phi_null=None, phi_null_c=None,
+                               U=None, _U_halos=None, _work={}, mg=None)
         for v in list(self.info.values()):
             if isinstance(v, MG):
                 v.close()
@@ -493,11 +540,7 @@ def make_single_precision(mg: "MG") -> "MG":
         l32.matrix_free = lv.matrix_free
         if lv.U is not None:
             l32.U = lv.U.to(c64)
-            if lv.distributed:
-                l32._U_lo = lv._U_lo.to(c64)
-                l32.U_lo_ptr = l32._U_lo.data_ptr()
-            else:
-                l32.U_lo_ptr = l32.U.data_ptr() + (l32.Ly - 1) * l32.L * 2 * l32.U.element_size()
+            l32.bind_link_halos(None if lv._U_halos is None else tuple(h.to(c64) for h in lv._U_halos))
     return m32
 
 
@@ -528,6 +571,7 @@ def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
         raise MG2DError("compute_coarse_matrix needs the stored fine operator")
     lvl_c.D = torch.empty((lvl_c.S, 5, nc, nc), dtype=mg.tdtype, device=mg.device)
     lvl_c.D0inv = None
+    lvl_c.M = None
     P = lvl_P.phi_null
     p_lo, p_hi = lvl_f._halo(P, 1, nc * nf)          # projector rows below / above the strip (or the periodic wrap)
     if lvl_f.distributed and not lvl_c.distributed:

@@ -92,6 +92,24 @@ int mg2d_wilson_relax_rb(mg2d_ctx*, void* phi, const void* phi_lo, const void* p
                          const void* U_lo, const void* r, double mass, int Lx, int Ly, int colour, int yoff,
                          int dtype, void* stream);
 
+/* One FULL red-black sweep (colour 0, then colour 1) of the matrix-free Wilson operator in a single pass, OUT OF PLACE
+ * (out != in): every phi / r / link element is read once and every result written once (128 B/site in complex128
+ * instead of ~224 B moved by two half-sweep launches).  Needs the neighbour data two rows deep: in_lo2 = rows
+ * (-2, -1), in_hi2 = rows (Ly, Ly+1) of `in`; U_lo2 = link rows (-2, -1), U_hi = link row Ly; r_lo / r_hi = rows
+ * -1 / Ly of r (r == NULL: r = 0).  On one GPU these are the periodic wrap rows of the arrays themselves. */
+int mg2d_wilson_relax_rb2(mg2d_ctx*, void* out, const void* in, const void* in_lo2, const void* in_hi2,
+                          const void* U, const void* U_lo2, const void* U_hi, const void* r, const void* r_lo,
+                          const void* r_hi, double mass, int Lx, int Ly, int yoff, int dtype, void* stream);
+
+/* The same half sweep on pre-multiplied hopping blocks M[s][k-1][j][i] = -D0inv(s) D_k(s), k = 1..4 (built once by
+ * mg2d_premultiply): phi(s) <- sum_k M_k(s) phi(s+d_k) + c(s), c = D0inv r.  4 blocks per updated site instead of 5.
+ * cmode 0: r = 0; 1: first sweep of a relax call (c computed from D0inv, r and stored in cbuf[nvec][S][n]);
+ * 2: c read from cbuf. */
+int mg2d_premultiply(mg2d_ctx*, void* M, const void* D, const void* D0inv, int n, long long nsites, int dtype, void* stream);
+int mg2d_relax_rb_pm(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* M, const void* D0inv,
+                     const void* r, void* cbuf, int cmode, int n, int Lx, int Ly, int colour, int yoff, int dtype,
+                     int nvec, long long vstride, long long hstride, void* stream);
+
 /* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
  * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64
  * operator); fields and arithmetic stay fp32.  n in {8,16,32}.  Mixed-precision option, no reference counterpart. */
@@ -196,6 +214,22 @@ int mg2d_ipc_open(mg2d_ctx*, const void* handle64, void** ptr);
 int mg2d_halo_exchange(mg2d_ctx*, const void* first, const void* last, long long src_stride_bytes, long long row_bytes,
                        int nvec, void* next_lo, void* prev_hi, void* slot_mine, void* slot_prev, void* slot_next,
                        void* stream);
+
+/* ---- inputs generated on the device (the reference draws from std::mt19937 / reads link files) ------ */
+/* out[e] = (lo + (hi-lo) u(seed, stream_id, offset+e), 0): counter-based uniform numbers (splitmix64 of the key), so a
+ * strip starting at global element `offset` holds what the whole field holds there (f_init_near_null_vector,
+ * S6/modules_indiv.h:52-68, for lattices beyond the sequential mt19937 stream; mirrored by oracle counter_uniform). */
+int mg2d_fill_uniform(mg2d_ctx*, void* out, long long nelem, long long offset, unsigned long long seed,
+                      unsigned long long stream_id, double lo, double hi, int dtype, void* stream);
+/* One checkerboard half-update (sites with (x+y)%2 == parity, direction mu) of compact-U(1) Wilson-action Metropolis on
+ * the phases theta[s][2] (doubles); proposal theta + (2u1-1) delta, accept if u2 < exp(-dS); u1, u2 = counter numbers of
+ * streams 2*tag, 2*tag+1 at index s.  Produces the configurations S6/gauge.h:88-110 reads from files it does not ship. */
+int mg2d_gauge_metropolis(mg2d_ctx*, double* theta, int L, double beta, double delta, int mu, int parity,
+                          unsigned long long seed, unsigned long long tag, void* stream);
+/* Gauge::f_plaquette (S6/gauge.h:50-63): out[0..1] = sum_s U_x(s) U_y(s+x) conj(U_x(s+y)) conj(U_y(s)) (re, im). */
+int mg2d_plaquette(mg2d_ctx*, const void* U, int L, int dtype, double* out, void* stream);
+/* U[e] = polar(1, theta[e]) (S6/gauge.h:106) */
+int mg2d_phases_to_links(mg2d_ctx*, void* U, const double* theta, long long nelem, int dtype, void* stream);
 
 /* ---- real scalar Laplace geometric MG, BASELINE config 1 (S2) -------------------------------------------- */
 /* relax (S2:46-72): num_iter lexicographic GS sweeps phi = scale (sum nbrs - b a^2), wavefront order. */

@@ -45,6 +45,62 @@ CASES = [
 ]
 
 
+# Full-size cases (BASELINE configs[2]: Wilson 256^2 near-critical, non-telescoping): the reference needs ~6 min and
+# writes ~2.4 GB of per-iteration text, so only the LAST row of results_phi.txt and the head of the near-null file are kept.
+# m_crit of this configuration is -0.0163 (smallest real part of spec D(0), scipy eigs): m = -0.01 is 0.006 above it.
+LARGE_CASES = [
+    ("big_s6_wilson256_ntl4_nearcrit", "wilson", 256, 3, 2, -0.01, 3, 1, 4, 50),
+]
+
+
+def last_line(path):
+    with open(path, "rb") as f:
+        f.seek(0, 2)
+        end = f.tell()
+        pos = end - 2
+        while pos > 0:
+            f.seek(pos)
+            if f.read(1) == b"\n":
+                break
+            pos -= 1
+        f.seek(pos + 1 if pos > 0 else 0)
+        return f.read().decode()
+
+
+def make_large(reuse=None):
+    """reuse: a directory that already holds run/ of the case (skips the 6-minute reference run)."""
+    for name, stencil, L, ni, blk, m, nl, tf, nco, sweeps in LARGE_CASES:
+        exe = os.path.join(ROOT, "oracle", "_ref", "s6_mgrid_ntl")
+        theta = O.gauge_quenched_phases(L, 32.0, sweeps=sweeps, seed=1234)
+        argv = [str(L), str(ni), str(blk), "1", repr(m), str(nl), str(tf), str(nco)]
+        d = reuse or tempfile.mkdtemp()
+        run = os.path.join(d, "run")
+        if not reuse:
+            os.makedirs(run)
+            os.makedirs(os.path.join(d, "gauge_config_files"))
+            O.write_phase_file(os.path.join(d, "gauge_config_files", f"phase_{L}_b32.0.dat"), theta, L)
+            with open(os.path.join(run, "out.txt"), "w") as fo:
+                subprocess.run([exe] + argv, cwd=run, stdout=fo, timeout=3600)
+        out = open(os.path.join(run, "out.txt")).read()
+        iters = int(re.search(r"Ans (\d+)", out).group(1))
+        resmag = [float(x) for x in re.findall(r"At iteration \d+, the mag residue is (\S+)", out)][1:]
+        f = last_line(os.path.join(run, "results_phi.txt")).rstrip().rstrip(",").split(",")
+        phi = np.array([complex(float(x.split("+i")[0]), float(x.split("+i")[1])) for x in f[1:]])
+        phi = phi.reshape(L, L, 2).transpose(1, 0, 2).reshape(L * L, 2)
+        head = []
+        with open(os.path.join(run, f"Near-null_L{L}_blk{blk}_ndof4.txt")) as fn:
+            for _ in range(4096 * 4 * 2):
+                a, b = fn.readline().strip().split("+i")
+                head.append(float(a) + 1j * float(b))
+        rows = open(os.path.join(run, "results_NTL_weights.txt")).read().strip().split("\n")
+        w = np.array([[complex(float(x.split("+i")[0]), float(x.split("+i")[1])) for x in r.rstrip(",").split(",")[1:]] for r in rows])
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), argv=np.array(argv), stencil=stencil,
+                            gauge=np.array([L, 32.0, sweeps, 1234]), theta_checksum=float(np.sum(theta * np.arange(1, theta.size + 1).reshape(theta.shape))),
+                            iters=iters, resmag=np.array(resmag), phi_final=phi, last_row_iter=int(f[0]),
+                            null0_head=np.array(head).reshape(4096, 4, 2), ntl_weights=w)
+        print(f"{name}: iters {iters} final printed residual {resmag[-1]}")
+
+
 def parse_cplx_rows(path, L, n):
     rows = open(path).read().strip().split("\n")
     out = []
@@ -90,4 +146,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--large":
+        make_large(sys.argv[2] if len(sys.argv) > 2 else None)
+    else:
+        main()

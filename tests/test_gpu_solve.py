@@ -115,6 +115,29 @@ def test_config3_wilson256_ntl_fullsize():
     assert np.all(np.isfinite(w)) and abs(w.sum()) > 0.05                 # min-res weights are in use
 
 
+def test_config3_matches_reference_run():
+    """BASELINE configs[2] at its stated size against the reference ITSELF: tests/golden/big_s6_wilson256_ntl4_nearcrit.npz was
+    written by the unmodified S6 program (`./a.out 256 3 2 1 -0.01 3 1 4`, 102 cycles, 6 min on one core; make_golden.py
+    --large).  Same links, same mt19937 start, same lexicographic GS / 500-sweep near-null vectors / 4-copy min-res cycle on
+    the GPU: identical iteration count, printed residual history, NTL weights and final phi."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "big_s6_wilson256_ntl4_nearcrit.npz"))
+    L, beta, sweeps, seed = int(z["gauge"][0]), float(z["gauge"][1]), int(z["gauge"][2]), int(z["gauge"][3])
+    theta = O.gauge_quenched_phases(L, beta, sweeps=sweeps, seed=seed)
+    assert float(np.sum(theta * np.arange(1, theta.size + 1).reshape(theta.shape))) == pytest.approx(float(z["theta_checksum"]), rel=1e-12)
+    a = [str(x) for x in z["argv"]]
+    p = mg2d.make_params(L, float(a[4]), nlevels=int(a[5]), block=int(a[2]), n_smooth=int(a[1]), smoother="gs", ntl=True, n_copies=int(a[7]))
+    mg, info = mg2d.run_reference_flow(p, T(O.gauge_from_phases(theta)))
+    assert info["converged"] and info["iters"] == int(z["iters"]) == 102
+    printed = z["resmag"]
+    for k in range(len(printed)):
+        assert abs(info["resnorms"][k] - printed[k]) <= 5e-4 * printed[k] + 5e-15, (k, info["resnorms"][k], printed[k])
+    assert rel(mg.LVL[0].phi, z["phi_final"]) < 1e-9
+    assert np.max(np.abs(mg.LVL[0].phi_null[:4096].cpu().numpy() - z["null0_head"])) < 1e-8
+    w = np.array(info["ntl_weights"])
+    assert np.max(np.abs(w[:5] - z["ntl_weights"][:5])) < 2e-3 * np.max(np.abs(z["ntl_weights"][:5]))
+
+
 # config 4 shape at a size the oracle can follow: 8 null vectors, 4x4 aggregates
 def test_config4_shape_small():
     L = 64
