@@ -61,6 +61,47 @@ def quenched_phases(L: int, beta: float, sweeps: int = 200, seed: int = 1234, de
     return th.reshape(L * L, 2)
 
 
+def quenched_links_device(L: int, beta: float, sweeps: int = 200, seed: int = 1234, device: int | None = None,
+                          dtype: str = "complex128", return_phases: bool = False):
+    """The same checkerboard Metropolis as CUDA kernels of libmg2d_sm100.so (mg2d_gauge_metropolis: one launch per
+    half-update, counter-based random numbers keyed on (seed, half-update, site); mirrored draw for draw by
+    oracle.gauge_quenched_phases_counter) followed by mg2d_phases_to_links.  Returns U[L*L, 2] on the device
+    (and the phases theta[L*L, 2] when return_phases)."""
+    from . import _lib
+    from .mg import _DT, _stream
+    dev = torch.cuda.current_device() if device is None else device
+    ctx = _lib.Context(dev)
+    tdtype, dcode = _DT[dtype]
+    with torch.cuda.device(dev):
+        th = torch.zeros((L * L, 2), dtype=torch.float64, device=f"cuda:{dev}")
+        delta = min(math.pi, 2.0 / math.sqrt(beta))
+        for sw in range(sweeps):
+            for mu in (0, 1):
+                for par in (0, 1):
+                    ctx.call("mg2d_gauge_metropolis", th.data_ptr(), L, float(beta), float(delta), mu, par, seed,
+                             (sw * 2 + mu) * 2 + par, _stream())
+        th = torch.remainder(th + math.pi, 2 * math.pi) - math.pi
+        U = torch.empty((L * L, 2), dtype=tdtype, device=th.device)
+        ctx.call("mg2d_phases_to_links", U.data_ptr(), th.data_ptr(), 2 * L * L, dcode, _stream())
+        torch.cuda.synchronize()
+    ctx.close()
+    return (U, th) if return_phases else U
+
+
+def plaquette_device(U: torch.Tensor, L: int) -> complex:
+    """Gauge::f_plaquette (S6/gauge.h:50-63) as a fused reduction kernel (mg2d_plaquette)."""
+    from . import _lib
+    from .mg import _stream
+    dev = U.device.index
+    ctx = _lib.Context(dev)
+    out = torch.zeros(2, dtype=torch.float64, device=U.device)
+    with torch.cuda.device(dev):
+        ctx.call("mg2d_plaquette", U.data_ptr(), L, _lib.C128 if U.dtype == torch.complex128 else _lib.C64, out.data_ptr(), _stream())
+        o = out.cpu()
+    ctx.close()
+    return complex(o[0].item(), o[1].item()) / (L * L)
+
+
 def plaquette(U, L: int) -> complex:
     """Gauge::f_plaquette (S6/gauge.h:50-63): mean of U_x(s) U_y(s+x) U_x(s+y)^* U_y(s)^*."""
     U = torch.as_tensor(U).reshape(L, L, 2)

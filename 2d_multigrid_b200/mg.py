@@ -115,8 +115,10 @@ class Level:
             self.phi_null = mg.to_device(draw(self.S * self.nc * self.n).reshape(self.S, self.nc, self.n))
 
     def define_source(self):
-        """f_define_source (S6/level.h:55-59)."""
-        self.r[2 + 2 * self.mg.p.L, 0] = 5.0
+        """f_define_source (S6/level.h:55-59): r(site 2 + 2L)(0) = 5 -- a GLOBAL site; on a strip only its owner writes."""
+        s = 2 + 2 * self.mg.p.L - self.y0 * self.L
+        if 0 <= s < self.S:
+            self.r[s, 0] = 5.0
 
     # ---- operators ------------------------------------------------------------------------------------
     def compute_lvl0_matrix(self, U: torch.Tensor, store: bool = True):
@@ -353,13 +355,22 @@ class Level:
         self.allreduce(out[:1], "max")
         return float(out[0].item())
 
-    def compact_projector(self, drop_dense: bool = False):
+    def compact_projector(self, drop_dense: bool = False, check: bool = False):
         """Wilson levels: keep the non-zero chirality half of every row of phi_null (S6/level.h:236-245) in
         phi_null_c[s][ic][jf'] so that restriction / prolongation stream half the bytes."""
         if self.phi_null is None or self.mg.p.stencil != "wilson":
             return
         nc, nf = self.nc, self.n
         P = self.phi_null
+        if check:
+            # supplied vectors (gen_null = 0) need not have f_near_null's chirality structure: keep the dense projector
+            # (as the reference's f_restriction / f_prolongation do) unless the halves to be dropped are exactly zero
+            dropped = torch.stack([P[:, :nc // 2, nf // 2:].abs().max(), P[:, nc // 2:, :nf // 2].abs().max()]).max()
+            if self.distributed:
+                self.mg.comm.allreduce(dropped, "max")
+            if float(dropped.item()) != 0.0:
+                self.phi_null_c = None
+                return
         self.phi_null_c = torch.cat([P[:, :nc // 2, :nf // 2], P[:, nc // 2:, nf // 2:]], dim=1).contiguous()
         if drop_dense:
             self.phi_null = None
@@ -492,18 +503,19 @@ class MG:
         self.LVL[0].define_source()
 
     def init_fields(self, generator_seed: int | None = None):
-        """Device-side initialisation for lattices too large for the host RNG stream: phi = 0, r = 0,
-        phi_null ~ U(-pi, pi) from torch's generator."""
+        """Device-side initialisation for lattices too large for the host RNG stream: phi = 0, r = 0 and near-null
+        seeds phi_null ~ U(-pi, pi) (f_init_near_null_vector, S6/modules_indiv.h:52-68) from the COUNTER-based generator
+        (mg2d_fill_uniform) keyed on (seed, level, GLOBAL element index): a strip draws exactly the numbers the
+        single-GPU field holds at the same sites, so the hierarchy does not depend on the partition
+        (mirrored by oracle build_device_problem)."""
         seed = self.p.seed if generator_seed is None else generator_seed
-        rank = 0 if self.comm is None else self.comm.rank
         for lv in self.LVL:
-            g = torch.Generator(device=self.device)
-            # strips draw rank-specific seeds; replicated levels must be identical on every rank
-            g.manual_seed(seed + 7919 * lv.lvl + (104729 * (rank + 1) if lv.distributed else 0))
             lv.phi, lv.r = lv.new_field(), lv.new_field()
             if lv.lvl != self.p.nlevels:
-                re = (torch.rand((lv.S, lv.nc, lv.n), generator=g, dtype=torch.float64, device=self.device) * 2 - 1) * math.pi
-                lv.phi_null = re.to(self.tdtype)
+                lv.phi_null = torch.empty((lv.S, lv.nc, lv.n), dtype=self.tdtype, device=self.device)
+                per_site = lv.nc * lv.n
+                self.ctx.call("mg2d_fill_uniform", _ptr(lv.phi_null), lv.S * per_site, lv.y0 * lv.L * per_site, seed, lv.lvl,
+                              -math.pi, math.pi, self.dcode, _stream())
 
     def set_gauge(self, U):
         """U: the full link field [L*L, 2] (each strip keeps its own rows) or already the local rows."""
@@ -619,10 +631,11 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
     mg.info["ortho_worst"] = worst
     if p.stencil == "wilson" and p.chiral_transfer:
         for lvl in range(p.nlevels):
-            mg.LVL[lvl].compact_projector()
+            mg.LVL[lvl].compact_projector(check=(gen_null != 1))
     if p.matrix_free:   # the stored level-0 operator was only needed for the Galerkin product
         mg.LVL[0].D = None
         mg.LVL[0].D0inv = None
+        mg.LVL[0].M = None
         mg.LVL[0].matrix_free = True
 
 

@@ -288,10 +288,8 @@ def main():
 
     # ---- inputs (not timed): links, critical mass, hierarchy ---------------------------------------------
     t0 = time.time()
-    th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=60, seed=1234, device=str(dev))
-    U = torch.exp(1j * th).to(torch.complex128)
-    del th
-    plaq = mg2d.gauge.plaquette(U, L).real
+    U = mg2d.gauge.quenched_links_device(L, 6.0, sweeps=60, seed=1234, device=local)     # Metropolis + plaquette kernels (N1)
+    plaq = mg2d.gauge.plaquette_device(U, L).real
     if rank == 0:
         print(f"# links {L}^2 beta=6 plaquette {plaq:.4f} ({time.time()-t0:.1f}s)", file=sys.stderr)
     t0 = time.time()
@@ -326,7 +324,7 @@ def main():
         torch.cuda.synchronize()
 
     def one_solve():
-        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4)
+        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1)
 
     # ---- device-resident steps ------------------------------------------------------------------------
     log("warm-up solves")
@@ -365,7 +363,7 @@ def main():
     log(f"c128 {ms:.1f} ms; mixed-precision leg")
     # ---- the same solve with the V-cycle preconditioner in complex64 (outer GCR / residual stay complex128) ----
     def mixed_solve():
-        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4, precond_dtype="complex64")
+        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1, precond_dtype="complex64")
     for _ in range(3):
         xm, info_m = mixed_solve()
     barrier()
@@ -383,7 +381,7 @@ def main():
     log(f"mixed {ms_mixed:.1f} ms; e2e leg")
     # ---- ... and with that copy's coarse operators stored in half precision (fp32 arithmetic) -------------------
     def half_solve():
-        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4, precond_dtype="complex64+half")
+        return mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1, precond_dtype="complex64+half")
     for _ in range(3):
         xh, info_h = half_solve()
     barrier()
@@ -402,7 +400,7 @@ def main():
     # ---- end to end: host rhs -> H2D -> solve -> D2H solution -----------------------------------------------
     def e2e_solve():
         r = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev, non_blocking=True)
-        xx, inf = mg2d.solve(mg, rhs=r, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=4)
+        xx, inf = mg2d.solve(mg, rhs=r, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1)
         if comm is not None:
             mg.gather_field(xx, x_host)
         else:
@@ -433,13 +431,19 @@ def main():
     t_apply = time_kernel(lambda: lv0.apply_D(b_, a), 20, flush)
     kern.append(("wilson_march_kernel<double> (D-apply, matrix-free)", 96.0 * S0, t_apply))
     lv0.phi.copy_(a)
-    t_rb0 = time_kernel(lambda: lv0.relax(1, smoother="rbgs"), 10, flush)
-    kern.append(("wilson_rb_kernel<double> x2 (one red-black GS sweep, level 0)", 160.0 * S0, t_rb0))
+    t_rb0 = time_kernel(lambda: lv0.relax(2, smoother="rbgs"), 10, flush) / 2
+    kern.append(("wilson_rb2_kernel<double> (one red-black GS sweep, both colours in one pass, level 0)", 128.0 * S0, t_rb0))
     if p.nlevels >= 1:
         l1 = mg.LVL[1]
         n1 = l1.n
-        t_rb1 = time_kernel(lambda: l1.relax(1, smoother="rbgs"), 10, flush if l1.S * n1 * n1 * 96 < 2e8 else None)
-        kern.append((f"stencil_rb_kernel<double,{n1}> x2 (one red-black GS sweep, level 1)", (4 * n1 * n1 + n1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
+        big = l1.S * n1 * n1 * 96 >= 2e8            # operator >> L2: no explicit flush needed
+        t_rb1a = time_kernel(lambda: l1.relax(1, smoother="rbgs"), 10, None if big else flush)
+        t_rb1b = time_kernel(lambda: l1.relax(3, smoother="rbgs"), 6, None if big else flush)
+        t_rb1 = (t_rb1b - t_rb1a) / 2
+        kern.append((f"stencil_rb_pm_kernel<double,{n1},1,2> x2 (one red-black GS sweep on pre-multiplied blocks, level 1)",
+                     (4 * n1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
+        kern.append((f"stencil_rb_pm_kernel<double,{n1},1,1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
+                     (5 * n1 * n1 + 4 * n1) * 16.0 * l1.S, t_rb1a))
         c, d_ = l1.new_field(), l1.new_field()
         c.normal_()
         t_ap1 = time_kernel(lambda: l1.apply_D(d_, c), 10, flush if l1.S * n1 * n1 * 80 < 2e8 else None)
@@ -456,7 +460,7 @@ def main():
         return
     table = [{"kernel": k, "bytes": by, "ms": t, "gbs": by / t / 1e6, "frac": by / t / 1e6 / hbm} for k, by, t in kern]
     # share of one V-cycle (nu = 4 pre + 4 post sweeps per level) taken by the level-1 smoother, from these timings
-    dom = max(table[1:3], key=lambda r: r["ms"]) if len(table) > 2 else table[0]
+    dom = table[2] if len(table) > 2 else table[0]      # level-1 smoother sweep: the largest share of a solve
     dapply = table[0]
     # dram bytes per launch from the committed ncu capture (profiles/traffic_L1024.json) apply to the L=1024 workload
     traffic = None

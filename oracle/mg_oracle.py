@@ -43,6 +43,22 @@ class StdMT19937:
         return canon * (np.pi - (-np.pi)) + (-np.pi)
 
 
+def counter_uniform(seed: int, stream: int, start: int, n: int, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
+    """Counter-based uniform numbers (ours; mirrored bit for bit by mg2d_fill_uniform / mg2d_gauge_metropolis): element e is
+    a splitmix64 hash of (seed, stream, start + e), so any sub-range of a field can be drawn independently -- strips of a
+    domain-decomposed lattice get exactly the numbers the whole lattice gets at the same global index."""
+    M = (1 << 64) - 1
+    with np.errstate(over="ignore"):
+        idx = np.arange(start + 1, start + n + 1, dtype=np.uint64)
+        base = np.uint64((seed * 0x9E3779B97F4A7C15 + stream * 0xD1B54A32D192ED03) & M)
+        z = base + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return lo + (hi - lo) * u
+
+
 # --------------------------------------------------------------------------------------------------
 # params  (S6/params.h:38-128)
 # --------------------------------------------------------------------------------------------------
@@ -215,6 +231,38 @@ def gauge_quenched_phases(L: int, beta: float, sweeps: int = 200, seed: int = 12
                 new = old + rng.uniform(-delta, delta, size=old.shape)
                 dS = staple_action(th, mu, new) - staple_action(th, mu, old)
                 acc = mask & (rng.random(old.shape) < np.exp(-dS))
+                th[..., mu] = np.where(acc, new, old)
+    th = (th + np.pi) % (2 * np.pi) - np.pi
+    return th.reshape(L * L, 2)
+
+
+def gauge_quenched_phases_counter(L: int, beta: float, sweeps: int = 200, seed: int = 1234) -> np.ndarray:
+    """The same checkerboard Metropolis with the counter-based generator (stream 2*tag / 2*tag+1 at index s for the
+    proposal / acceptance draw of half-update tag = (sweep*2 + mu)*2 + parity): the algorithm mg2d_gauge_metropolis
+    runs on the device, draw for draw."""
+    th = np.zeros((L, L, 2))  # th[y, x, dir]
+    yy, xx = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+    delta = min(np.pi, 2.0 / math.sqrt(beta))
+    sh = lambda a, d, k: np.roll(a, -k, axis=1 if d == 0 else 0)  # value at x + k*d_hat
+
+    def action(th, mu, t_mu):
+        nu = 1 - mu
+        t_nu, o_mu = th[..., nu], th[..., mu]
+        p_up = t_mu + sh(t_nu, mu, 1) - sh(o_mu, nu, 1) - t_nu
+        p_dn = sh(t_nu, nu, -1) + t_mu - sh(sh(t_nu, nu, -1), mu, 1) - sh(o_mu, nu, -1)
+        return -beta * (np.cos(p_up) + np.cos(p_dn))
+
+    for sw in range(sweeps):
+        for mu in (0, 1):
+            for par in (0, 1):
+                tag = (sw * 2 + mu) * 2 + par
+                mask = ((xx + yy) % 2) == par
+                old = th[..., mu]
+                u1 = counter_uniform(seed, 2 * tag, 0, L * L).reshape(L, L)
+                u2 = counter_uniform(seed, 2 * tag + 1, 0, L * L).reshape(L, L)
+                new = old + (2.0 * u1 - 1.0) * delta
+                dS = action(th, mu, new) - action(th, mu, old)
+                acc = mask & (u2 < np.exp(-dS))
                 th[..., mu] = np.where(acc, new, old)
     th = (th + np.pi) % (2 * np.pi) - np.pi
     return th.reshape(L * L, 2)
@@ -717,6 +765,22 @@ def build_reference_problem(p: Params, U: np.ndarray, seed: int = 4302529):
     NTL = [[Level() for _ in range(4)] for _ in range(p.nlevels + 1)]
     init_NTL(NTL, p, gen)
     LVL[0].define_source(p)
+    LVL[0].compute_lvl0_matrix(U, p)
+    return LVL, NTL
+
+
+def build_device_problem(p: Params, U: np.ndarray, seed: int = 4302529):
+    """Initial data of the large-lattice mode (mirrors MG.init_fields of the CUDA path): phi = 0, r = 0, near-null seeds
+    phi_null[s, ic, jf] = counter_uniform(seed, stream=level, global element index) in (-pi, pi), real."""
+    LVL = [Level() for _ in range(p.nlevels + 1)]
+    for lvl in range(p.nlevels + 1):
+        S, n = p.size[lvl] ** 2, p.n_dof[lvl]
+        LVL[lvl].phi = np.zeros((S, n), dtype=C128)
+        LVL[lvl].r = np.zeros((S, n), dtype=C128)
+        if lvl != p.nlevels:
+            nc = p.n_dof[lvl + 1]
+            LVL[lvl].phi_null = counter_uniform(seed, lvl, 0, S * nc * n, -np.pi, np.pi).reshape(S, nc, n).astype(C128)
+    NTL = [[Level() for _ in range(4)] for _ in range(p.nlevels + 1)]
     LVL[0].compute_lvl0_matrix(U, p)
     return LVL, NTL
 

@@ -126,10 +126,17 @@ def test_block_stencil_all_sizes(n):
                    ("mr", lambda o: o.relax_mr(L, 2))):
         o2 = copy.deepcopy(lvo)
         fn(o2)
-        phi0 = lv.phi.clone()
-        lv.relax(2, smoother=sm)
-        assert rel(lv.phi, o2.phi) < 1e-11, sm
-        lv.phi.copy_(phi0)
+        for premul in ((True, False) if sm == "rbgs" else (True,)):     # rbgs: pre-multiplied blocks -D0^-1 D_k and plain blocks
+            mg.premul = premul
+            phi0 = lv.phi.clone()
+            lv.relax(2, smoother=sm)
+            assert rel(lv.phi, o2.phi) < 1e-11, (sm, premul)
+            lv.phi.copy_(phi0)
+    mg.premul = True
+    if n <= 16:
+        lv._ensure_M()
+        Mref = -np.einsum("sil,sklj->skij", np.linalg.inv(Dref[:, 0]), Dref[:, 1:])
+        assert rel(lv.M.transpose(-1, -2), Mref) < 1e-11
     # batched red-black path (4 vectors share one stream of the operator) == vector-at-a-time path
     for nvec in (4, 8):
         V = T(crand(rng, nvec, S, n))
@@ -252,3 +259,88 @@ def test_error_behaviour():
         mg.ctx.call("mg2d_wilson_apply", None, v.data_ptr(), v.data_ptr(), v.data_ptr(), v.data_ptr(), v.data_ptr(),
                     None, 0.1, 8, 8, 0, 0, None, s)
     assert mg.ctx.launches > 0
+
+
+@pytest.mark.parametrize("L", [4, 6, 34, 64, 130, 256])
+def test_wilson_two_colour_sweep(L):
+    """mg2d_wilson_relax_rb2 (both colours in one pass, out of place) vs oracle Level.relax_rb and vs the two half-sweep
+    launches it replaces; ragged sizes exercise partial tiles / chunks and the periodic wrap of the two-row halos."""
+    rng = np.random.default_rng(L)
+    po, LVLo, _, p, mg, U = _pair(L, -0.03, nlevels=1)
+    lv = mg.LVL[0]
+    lv.matrix_free = True
+    phi0 = lv.phi.clone()
+    for nsweep in (1, 2, 3):
+        o2 = copy.deepcopy(LVLo[0])
+        o2.relax_rb(L, nsweep)
+        mg.two_colour = True
+        lv.phi.copy_(phi0)
+        lv.relax(nsweep, smoother="rbgs")
+        assert rel(lv.phi, o2.phi) < 1e-11, nsweep
+        got = lv.phi.clone()
+        mg.two_colour = False
+        lv.phi.copy_(phi0)
+        lv.relax(nsweep, smoother="rbgs")
+        assert rel(got, lv.phi.cpu().numpy()) < 1e-13, nsweep
+    # r = 0 (near-null relaxation), batched
+    V = T(crand(rng, 2, L * L, 2))
+    mg.two_colour = True
+    Va = V.clone(); lv.relax(2, phi=Va, r=None, smoother="rbgs")
+    mg.two_colour = False
+    Vb = V.clone(); lv.relax(2, phi=Vb, r=None, smoother="rbgs")
+    assert rel(Va, Vb.cpu().numpy()) < 1e-13
+    mg.two_colour = True
+
+
+def test_wilson_two_colour_sweep_complex64():
+    L = 64
+    U = O.gauge_gaussian(L, width=0.4, seed=9)
+    outs = {}
+    for two in (True, False):
+        p = mg2d.make_params(L, 0.05, nlevels=0, smoother="rbgs", dtype="complex64")
+        mg = mg2d.MG(p)
+        mg.init_reference_fields()
+        mg.LVL[0].compute_lvl0_matrix(T(U).to(torch.complex64), store=False)
+        mg.two_colour = two
+        mg.LVL[0].relax(3)
+        outs[two] = mg.LVL[0].phi.cpu().numpy()
+    assert np.max(np.abs(outs[True] - outs[False])) < 2e-5 * np.max(np.abs(outs[False]))
+
+
+def test_counter_rng_and_gauge_kernels():
+    """mg2d_fill_uniform == oracle counter_uniform bit for bit (any offset); mg2d_gauge_metropolis == the oracle's counter
+    Metropolis draw for draw; mg2d_plaquette == Gauge::f_plaquette."""
+    p = mg2d.make_params(16, 0.1, nlevels=0, matrix_free=False)
+    mg = mg2d.MG(p)
+    out = torch.empty(1000, dtype=torch.complex128, device="cuda")
+    for seed, stream, off in ((4302529, 0, 0), (7, 3, 123456789012), (2**40 + 5, 17, 999)):
+        mg.ctx.call("mg2d_fill_uniform", out.data_ptr(), 1000, off, seed, stream, -np.pi, np.pi, mg.dcode, torch.cuda.current_stream().cuda_stream)
+        want = O.counter_uniform(seed, stream, off, 1000, -np.pi, np.pi)
+        got = out.cpu().numpy()
+        assert np.array_equal(got.real, want) and not got.imag.any()
+    for L, beta, sweeps in ((16, 6.0, 12), (32, 32.0, 8)):
+        Ud, th = mg2d.gauge.quenched_links_device(L, beta, sweeps=sweeps, seed=1234, return_phases=True)
+        want = O.gauge_quenched_phases_counter(L, beta, sweeps=sweeps, seed=1234)
+        assert np.max(np.abs(th.cpu().numpy() - want)) < 1e-12
+        Uo = O.gauge_from_phases(want)
+        assert rel(Ud, Uo) < 1e-14
+        pd, po_ = mg2d.gauge.plaquette_device(Ud, L), O.plaquette(Uo, L)
+        assert abs(pd - po_) < 1e-13
+        assert 0.3 < pd.real < 1.0
+
+
+def test_device_init_fields_match_oracle():
+    """MG.init_fields (counter-seeded near-null start) == oracle build_device_problem, and the resulting hierarchy too."""
+    L = 32
+    U = O.gauge_gaussian(L, width=0.4, seed=9)
+    po = O.Params(L=L, num_iters=2, block=4, m=0.01, nlevels=1, stencil="wilson", smoother="rbgs", n_dof_scale=8, null_iters=12)
+    LVLo, NTLo = O.build_device_problem(po, U)
+    p = mg2d.make_params(L, 0.01, nlevels=1, block=4, n_null=4, n_smooth=2, smoother="rbgs", null_iters=12)
+    mg = mg2d.MG(p)
+    mg.init_fields()
+    assert np.array_equal(mg.LVL[0].phi_null.cpu().numpy(), LVLo[0].phi_null)
+    mg.set_gauge(T(U))
+    mg2d.compute_near_null(mg)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    assert rel(mg.LVL[0].phi_null, LVLo[0].phi_null) < 1e-10
+    assert rel(mg2d.D_to_reference_layout(mg.LVL[1].D), LVLo[1].D) < 1e-10

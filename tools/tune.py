@@ -7,8 +7,8 @@ from importlib import import_module
 critical = import_module("2d_multigrid_b200.critical")
 torch.cuda.set_device(0); dev = torch.device("cuda", 0)
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-th = mg2d.gauge.quenched_phases(L, 6.0, sweeps=60, seed=1234, device="cuda"); U = torch.exp(1j * th).to(torch.complex128); del th
-mcrit = {4096: -0.06552, 1024: -0.06838}.get(L)
+U = mg2d.gauge.quenched_links_device(L, 6.0, sweeps=60, seed=1234)
+mcrit = float(os.environ["MG2D_MCRIT"]) if "MG2D_MCRIT" in os.environ else None
 if mcrit is None:
     mcrit, _ = critical.estimate_critical_mass(U, lambda m: bench.workload_params(mg2d, L, m), iters=4, refine=3)
 p = bench.workload_params(mg2d, L, mcrit + 1e-3)
@@ -19,7 +19,7 @@ def run(pre, post, mixed, restart=8):
     for m in [mg] + ([mg.info["single"]] if "single" in mg.info else []):
         m.p.pre, m.p.post = list(pre), list(post)
         m.info.pop("precond_graph", None); m.info.pop("cycle_graph", None)
-    kw = dict(rhs=rhs, tol=1e-10, outer="gcr", restart=restart, use_graph=True, check_every=4, max_iters=120)
+    kw = dict(rhs=rhs, tol=1e-10, outer="gcr", restart=restart, use_graph=True, check_every=1, max_iters=120)
     if mixed: kw["precond_dtype"] = "complex64"
     x, info = mg2d.solve(mg, **kw)
     if mixed:   # the shadow was created with the default counts on first use: re-apply and re-run
