@@ -27,15 +27,15 @@ SIGNATURES = {
     "mg2d_relax_gs": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp],
     "mg2d_relax_rb": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
     "mg2d_wilson_relax_rb": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _i, _vp],
-    "mg2d_wilson_relax_rb2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp],
+    "mg2d_wilson_relax_rb2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp],
     "mg2d_premultiply": [_vp, _vp, _vp, _i, _ll, _i, _vp],
-    "mg2d_relax_rb_pm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
+    "mg2d_relax_rb_pm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp, _vp],
     "mg2d_relax_rb_half": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mg2d_to_half": [_vp, _vp, _ll, _vp],
     "mg2d_axpy_ratio2": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _i, _vp],
     "mg2d_gcr_dots": [_vp, _ll, _i, _vp, _ll, _i, _vp, _vp],
     "mg2d_gcr_ortho": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp],
-    "mg2d_gcr_step": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp],
+    "mg2d_gcr_step": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp],
     "mg2d_mr_update": [_vp, _vp, _vp, _vp, _d, _ll, _i, _i, _ll, _vp],
     "mg2d_axpy": [_vp, _vp, _d, _d, _vp, _ll, _i, _vp],
     "mg2d_zero": [_vp, _ll, _i, _vp],
@@ -55,6 +55,12 @@ SIGNATURES = {
     "mg2d_coarse_matrix": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mg2d_minres_solve": [_vp, _vp, _i, _vp, _vp],
     "mg2d_scale_phi": [_vp, _vp, _ll, _vp, _i, _ll, _i, _vp],
+    "mg2d_comm_create": [_i, _i, C.POINTER(_vp), C.POINTER(_vp)],
+    "mg2d_comm_attach": [_vp],
+    "mg2d_comm_reduce": [_i],
+    "mg2d_comm_error": [_vp, C.POINTER(_ll)],
+    "mg2d_allreduce": [_vp, _i, _vp],
+    "mg2d_halo_errors": [_vp, _i, C.POINTER(_ll)],
     "mg2d_ipc_alloc": [_ll, C.POINTER(_vp), _vp],
     "mg2d_ipc_open": [_vp, C.POINTER(_vp)],
     "mg2d_halo_exchange": [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -74,7 +80,15 @@ PLAIN = {  # entry points without the uniform (ctx, ...) -> int shape
     "mg2d_destroy": ([_vp], _i),
     "mg2d_last_error": ([_vp], C.c_char_p),
     "mg2d_launch_count": ([_vp], _i),
+    "mg2d_comm_mailbox_bytes": ([], _i),
 }
+
+
+class HaloLink(C.Structure):
+    """mg2d_halo_link of include/mg2d.h."""
+    _fields_ = [("slot_mine", _vp), ("slot_prev", _vp), ("slot_next", _vp), ("push_next_lo", _vp), ("push_prev_hi", _vp),
+                ("wait", _i)]
+
 
 _lib = None
 

@@ -89,13 +89,13 @@ __global__ void __launch_bounds__(BL_THREADS) convert_kernel(cplx<TD>* __restric
 template <typename T>
 __global__ void __launch_bounds__(BL_THREADS)
 norm2_kernel(const cplx<T>* __restrict__ x, long long n, double* __restrict__ partials, unsigned int* __restrict__ counter,
-             double* __restrict__ out) {
+             double* __restrict__ out, XComm* xc) {
     double red[1] = {0.0};
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const cplx<T> v = __ldg(x + e);
         red[0] += (double)v.x * v.x + (double)v.y * v.y;
     }
-    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
 
 // one (i,j) pair per blockIdx.y; out[2*(i*ny+j)] = sum conj(x_i) y_j
@@ -222,7 +222,7 @@ extern "C" int mg2d_create(mg2d_ctx** out, int device) {
     if (prop.major != 10) return MG2D_EUNSUPPORTED;   // sm_100a only: no fallback path exists
     mg2d_ctx* c = new mg2d_ctx();
     c->device = device; c->launches = 0; c->num_sms = prop.multiProcessorCount; c->err[0] = 0;
-    c->partials = nullptr; c->counter = nullptr; c->status = nullptr;
+    c->partials = nullptr; c->counter = nullptr; c->status = nullptr; c->xcomm = nullptr; c->xreduce = 0;
     if (cudaMalloc(&c->partials, sizeof(double) * MG2D_MAX_PARTIALS * 4 * 64) != cudaSuccess ||
         cudaMalloc(&c->counter, sizeof(unsigned int) * 256) != cudaSuccess ||
         cudaMalloc(&c->status, sizeof(int) * 16) != cudaSuccess ||
@@ -314,9 +314,10 @@ extern "C" int mg2d_norm2(mg2d_ctx* ctx, const void* x, long long nelem, int dty
     if (!x || !out || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_norm2: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
     DISPATCH_T(dtype,
-        (norm2_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)x, nelem, ctx->partials, ctx->counter, out)),
-        (norm2_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)x, nelem, ctx->partials, ctx->counter, out)),
+        (norm2_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)x, nelem, ctx->partials, ctx->counter, out, xc)),
+        (norm2_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)x, nelem, ctx->partials, ctx->counter, out, xc)),
         "mg2d_norm2");
 }
 
@@ -383,7 +384,7 @@ constexpr int GCR_MAXJ = 8;
 template <typename T>
 __global__ void __launch_bounds__(BL_THREADS)
 gcr_dots_kernel(const cplx<T>* __restrict__ W, long long stride, int nj, const cplx<T>* __restrict__ w, long long n,
-                double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out) {
+                double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
     double red[2 * GCR_MAXJ];
 #pragma unroll
     for (int k = 0; k < 2 * GCR_MAXJ; ++k) red[k] = 0.0;
@@ -398,7 +399,7 @@ gcr_dots_kernel(const cplx<T>* __restrict__ W, long long stride, int nj, const c
             }
         }
     }
-    grid_reduce<2 * GCR_MAXJ, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+    grid_reduce<2 * GCR_MAXJ, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
 
 template <typename T>
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(BL_THREADS)
 gcr_ortho_kernel(cplx<T>* __restrict__ w, cplx<T>* __restrict__ z, const cplx<T>* __restrict__ r,
                  const cplx<T>* __restrict__ W, const cplx<T>* __restrict__ Z, long long stride, int nj,
                  const double* __restrict__ dots, const double* __restrict__ wn2, long long n,
-                 double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out) {
+                 double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
     using C = cplx<T>;
     C beta[GCR_MAXJ];
 #pragma unroll
@@ -430,18 +431,19 @@ gcr_ortho_kernel(cplx<T>* __restrict__ w, cplx<T>* __restrict__ z, const cplx<T>
         red[1] += (double)wv.x * rv.x + (double)wv.y * rv.y;       // <w, r> = conj(w) r
         red[2] += (double)wv.x * rv.y - (double)wv.y * rv.x;
     }
-    grid_reduce<4, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+    grid_reduce<4, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(BL_THREADS)
 gcr_step_kernel(cplx<T>* __restrict__ x, cplx<T>* __restrict__ r, const cplx<T>* __restrict__ z, const cplx<T>* __restrict__ w,
-                const double* __restrict__ wr, long long n, double* __restrict__ partials, unsigned int* __restrict__ counter,
-                double* __restrict__ out) {
+                const double* __restrict__ wr, double* __restrict__ wn2_slot, long long n, double* __restrict__ partials,
+                unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
     using C = cplx<T>;
     const double d = wr[0];                       // wr = { |w|^2, Re<w,r>, Im<w,r> } as written by gcr_ortho_kernel
     const C a = d > 0.0 ? mk<T>((T)(wr[1] / d), (T)(wr[2] / d)) : mk<T>(0, 0);
     const C na = mk<T>(-a.x, -a.y);
+    if (wn2_slot && blockIdx.x == 0 && threadIdx.x == 0) *wn2_slot = d;      // |w_slot|^2 for the projections of later iterations
     double red[1] = {0.0};
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         C xv = x[e], rv = r[e];
@@ -450,7 +452,7 @@ gcr_step_kernel(cplx<T>* __restrict__ x, cplx<T>* __restrict__ r, const cplx<T>*
         x[e] = xv; r[e] = rv;
         red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
     }
-    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x);
+    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
 }  // namespace
 
@@ -460,9 +462,10 @@ extern "C" int mg2d_gcr_dots(mg2d_ctx* ctx, const void* W, long long stride, int
     if (!W || !w || !out || nj < 1 || nj > GCR_MAXJ || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_dots: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
     DISPATCH_T(dtype,
-        (gcr_dots_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)W, stride, nj, (const double2*)w, nelem, ctx->partials, ctx->counter, out)),
-        (gcr_dots_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)W, stride, nj, (const float2*)w, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_dots_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)W, stride, nj, (const double2*)w, nelem, ctx->partials, ctx->counter, out, xc)),
+        (gcr_dots_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)W, stride, nj, (const float2*)w, nelem, ctx->partials, ctx->counter, out, xc)),
         "mg2d_gcr_dots");
 }
 
@@ -473,21 +476,23 @@ extern "C" int mg2d_gcr_ortho(mg2d_ctx* ctx, void* w, void* z, const void* r, co
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_ortho: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
     DISPATCH_T(dtype,
-        (gcr_ortho_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)w, (double2*)z, (const double2*)r, (const double2*)W, (const double2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out)),
-        (gcr_ortho_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)w, (float2*)z, (const float2*)r, (const float2*)W, (const float2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_ortho_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)w, (double2*)z, (const double2*)r, (const double2*)W, (const double2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out, xc)),
+        (gcr_ortho_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)w, (float2*)z, (const float2*)r, (const float2*)W, (const float2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out, xc)),
         "mg2d_gcr_ortho");
 }
 
-extern "C" int mg2d_gcr_step(mg2d_ctx* ctx, void* x, void* r, const void* z, const void* w, const double* wr, long long nelem,
-                             int dtype, double* out, void* stream) {
+extern "C" int mg2d_gcr_step(mg2d_ctx* ctx, void* x, void* r, const void* z, const void* w, const double* wr, double* wn2_slot,
+                             long long nelem, int dtype, double* out, void* stream) {
     if (!ctx) return MG2D_EINVAL;
     if (!x || !r || !z || !w || !wr || !out || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_step: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
     DISPATCH_T(dtype,
-        (gcr_step_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, (double2*)r, (const double2*)z, (const double2*)w, wr, nelem, ctx->partials, ctx->counter, out)),
-        (gcr_step_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, (float2*)r, (const float2*)z, (const float2*)w, wr, nelem, ctx->partials, ctx->counter, out)),
+        (gcr_step_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, (double2*)r, (const double2*)z, (const double2*)w, wr, wn2_slot, nelem, ctx->partials, ctx->counter, out, xc)),
+        (gcr_step_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, (float2*)r, (const float2*)z, (const float2*)w, wr, wn2_slot, nelem, ctx->partials, ctx->counter, out, xc)),
         "mg2d_gcr_step");
 }
 
@@ -500,30 +505,6 @@ extern "C" int mg2d_gcr_step(mg2d_ctx* ctx, void* x, void* r, const void* z, con
 // from a CUDA graph.  A bounded spin turns a lost peer into an error flag instead of a hang.
 // =========================================================================================================
 namespace {
-
-struct HaloSlot {            // one per (level, width, nvec, dtype); identical offsets on every rank
-    unsigned long long flag_lo, flag_hi;     // written by prev / next: epoch of the rows now in lo_buf / hi_buf
-    unsigned long long ack_prev, ack_next;   // written by prev / next: last epoch of MY rows they have consumed
-    unsigned long long epoch;                // local
-    unsigned long long error;
-    unsigned long long pad[2];
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
-    for (long long it = 0; it < (1ll << 24); ++it) {
-        if (ld_acquire_sys(p) >= want) return true;
-        __nanosleep(200);
-    }
-    return false;
-}
 
 // first/last: this rank's boundary rows (nvec pieces of row16 16-byte words, src_stride16 apart);
 // next_lo / prev_hi: the neighbours' halo buffers; slots: mine and the two neighbours'.
@@ -560,20 +541,36 @@ halo_exchange_kernel(const uint4* __restrict__ first, const uint4* __restrict__ 
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long t = atomicAdd(&mine->pad[0], 1ull);
+        if (!s_ok) atomicExch(&mine->error, 1ull);
+        const unsigned long long t = atomicAdd(&mine->ticket, 1ull);
         s_last = (t == (unsigned long long)gridDim.x - 1);
-        if (!s_ok) mine->error = 1;
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence_system();
-        mine->pad[0] = 0;
-        st_release_sys(&next->flag_lo, e + 1);
-        st_release_sys(&prev->flag_hi, e + 1);
-        const bool ok = spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
-        if (!ok) mine->error = 1;
+        mine->ticket = 0;
+        // a time-out anywhere in this launch poisons the exchange: the neighbours get an epoch they can recognise
+        // (all-ones) instead of stale rows published as fresh, and the error word stays set for the host to raise on
+        const bool failed = ld_acquire_sys(&mine->error) != 0ull;
+        if (failed) {
+            st_release_sys(&next->flag_lo, ~0ull);
+            st_release_sys(&prev->flag_hi, ~0ull);
+        } else {
+            st_release_sys(&next->flag_lo, e + 1);
+            st_release_sys(&prev->flag_hi, e + 1);
+            const bool ok = spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
+            if (!ok || ld_acquire_sys(&mine->flag_lo) == ~0ull || ld_acquire_sys(&mine->flag_hi) == ~0ull) mine->error = 1;
+        }
         mine->epoch = e + 1;
     }
+}
+
+// standalone all-reduce of n <= MG2D_XRED_MAX doubles in place (batched reductions that are not fused into their kernel)
+__global__ void __launch_bounds__(128) xcomm_allreduce_kernel(XComm* xc, double* buf, int n) {
+    __shared__ double s_v[MG2D_XRED_MAX];
+    if ((int)threadIdx.x < n) s_v[threadIdx.x] = buf[threadIdx.x];
+    __syncthreads();
+    xcomm_allreduce(xc, s_v, n, buf);
 }
 
 }  // namespace
@@ -612,4 +609,74 @@ extern "C" int mg2d_halo_exchange(mg2d_ctx* ctx, const void* first, const void* 
     halo_exchange_kernel<<<(nvec * (row_bytes / 16) > 4096 ? HX_CTAS : 1), HX_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)first, (const uint4*)last, src_stride_bytes / 16,
         row_bytes / 16, nvec, (uint4*)next_lo, (uint4*)prev_hi, (HaloSlot*)slot_mine, (HaloSlot*)slot_prev, (HaloSlot*)slot_next);
     return mg2d_check_launch(ctx, "mg2d_halo_exchange");
+}
+
+// ---- cross-GPU reductions fused into the kernels -------------------------------------------------------------------
+extern "C" int mg2d_comm_create(mg2d_ctx* ctx, int world, int rank, void* const* area_ptrs, void** desc_out) {
+    if (!ctx) return MG2D_EINVAL;
+    if (world < 1 || world > MG2D_MAX_RANKS || rank < 0 || rank >= world || !area_ptrs || !desc_out)
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_create: bad argument (at most 8 ranks)");
+    XComm h;
+    memset(&h, 0, sizeof(h));
+    h.world = world; h.rank = rank;
+    for (int q = 0; q < world; ++q) {
+        if (!area_ptrs[q]) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_create: null mailbox pointer");
+        h.area[q] = (XRedArea*)area_ptrs[q];
+    }
+    XComm* d = nullptr;
+    if (cudaMalloc(&d, sizeof(XComm)) != cudaSuccess || cudaMemcpy(d, &h, sizeof(XComm), cudaMemcpyHostToDevice) != cudaSuccess)
+        return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_comm_create: allocation failed");
+    *desc_out = d;
+    ctx->xcomm = d;
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_comm_attach(mg2d_ctx* ctx, void* desc) {
+    if (!ctx) return MG2D_EINVAL;
+    ctx->xcomm = (XComm*)desc;
+    if (!desc) ctx->xreduce = 0;
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_comm_reduce(mg2d_ctx* ctx, int on) {
+    if (!ctx) return MG2D_EINVAL;
+    if (on && !ctx->xcomm) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_reduce: no communicator attached");
+    ctx->xreduce = on ? 1 : 0;
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_comm_mailbox_bytes(void) { return (int)sizeof(XRedArea); }
+
+extern "C" int mg2d_comm_error(mg2d_ctx* ctx, void* desc, long long* out) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!desc || !out) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_error: bad argument");
+    XComm h;
+    if (cudaMemcpy(&h, desc, sizeof(XComm), cudaMemcpyDeviceToHost) != cudaSuccess) return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_comm_error: copy failed");
+    *out = (long long)h.error;
+    return MG2D_OK;
+}
+
+extern "C" int mg2d_allreduce(mg2d_ctx* ctx, double* buf, int n, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!buf || n < 1 || n > MG2D_XRED_MAX || !ctx->xcomm) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_allreduce: bad argument / no communicator");
+    xcomm_allreduce_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(ctx->xcomm, buf, n);
+    return mg2d_check_launch(ctx, "mg2d_allreduce");
+}
+
+// sum of the error words of `nslots` halo slots (64-byte records starting at `slots`)
+extern "C" int mg2d_halo_errors(mg2d_ctx* ctx, const void* slots, int nslots, long long* out) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!slots || nslots < 0 || !out) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_halo_errors: bad argument");
+    long long tot = 0;
+    if (nslots > 0) {
+        HaloSlot* h = new HaloSlot[nslots];
+        if (cudaMemcpy(h, slots, (size_t)nslots * sizeof(HaloSlot), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            delete[] h;
+            return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_halo_errors: copy failed");
+        }
+        for (int i = 0; i < nslots; ++i) tot += (long long)h[i].error;
+        delete[] h;
+    }
+    *out = tot;
+    return MG2D_OK;
 }

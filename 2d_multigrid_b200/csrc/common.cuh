@@ -9,6 +9,39 @@
 #define MG2D_MAX_PARTIALS 4096   // max CTAs contributing to one reduction
 #define MG2D_MAX_RED 64          // max doubles per reduction (batched dots)
 
+// ---- multi-GPU records living in the CUDA-IPC slabs (identical offsets on every rank) ---------------------------
+#define MG2D_MAX_RANKS 8
+#define MG2D_XRED_MAX 64         // doubles per cross-GPU reduction
+
+struct HaloSlot {            // one per exchanged field (level, width, depth); 64 bytes
+    unsigned long long flag_lo, flag_hi;     // written by prev / next: epoch of the rows now in my lo / hi halo buffer
+    unsigned long long ack_prev, ack_next;   // written by prev / next: last epoch of MY rows they have consumed
+    unsigned long long epoch;                // local: number of publishes done
+    unsigned long long error;                // local: a neighbour did not answer within the spin bound
+    unsigned long long ticket;               // local: CTAs of the running kernel that finished
+    unsigned long long pad;
+};
+
+struct XRedArea {            // all-reduce mailbox: every rank writes its partial sums into every peer's area
+    unsigned long long flag[2][MG2D_MAX_RANKS];              // [parity][source rank] = epoch of buf[parity][source]
+    double buf[2][MG2D_MAX_RANKS][MG2D_XRED_MAX];
+};
+
+struct XComm {               // local descriptor (plain device memory) of the rank's place among its peers
+    int world, rank;
+    unsigned long long epoch;                // all-reduces completed
+    unsigned long long error;
+    XRedArea* area[MG2D_MAX_RANKS];          // area[q] = rank q's mailbox (peer-mapped; area[rank] is local)
+};
+
+// what a stencil kernel needs to push its boundary rows to the strip neighbours and to wait for theirs (host struct
+// mg2d_halo_link of include/mg2d.h, resolved to typed pointers)
+struct HaloLinkDev {
+    HaloSlot* mine; HaloSlot* prev; HaloSlot* next;
+    void* push_next_lo; void* push_prev_hi;
+    int wait;
+};
+
 struct mg2d_ctx {
     int device;
     int launches;
@@ -16,6 +49,8 @@ struct mg2d_ctx {
     unsigned int* counter;   // last-block-done tickets, one per reduction "channel"
     int* status;
     int num_sms;
+    XComm* xcomm;            // multi-GPU: descriptor for reductions fused into the kernels (NULL on one GPU)
+    int xreduce;             // 1: reductions of the following calls are summed over all ranks inside the kernel
     char err[512];
 };
 
@@ -80,15 +115,71 @@ template <typename C> __device__ __forceinline__ C shfl_c(C v, int src, int widt
     v.x = __shfl_sync(0xffffffffu, v.x, src, width); v.y = __shfl_sync(0xffffffffu, v.y, src, width); return v;
 }
 
+// ---- system-scope flag accesses (peer memory over NVLink) ---------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded spin (~20 s): a lost peer becomes an error flag, never a hang
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
+    for (long long it = 0; it < (1ll << 27); ++it) {
+        if (ld_acquire_sys(p) >= want) return true;
+        __nanosleep(it < 64 ? 20 : 150);
+    }
+    return false;
+}
+
+// Sum `vals[0..nr)` (shared memory, block-uniform) over all ranks: every rank stores its numbers into every peer's
+// mailbox, raises the peer's flag, waits for all flags of its own mailbox and adds the contributions in rank order, so
+// all ranks obtain bit-identical results.  Called by ONE CTA (all its threads).  Two mailbox halves alternate: a rank
+// can only be one reduction ahead of its slowest peer (it needs that peer's contribution to finish the current one).
+__device__ __forceinline__ void xcomm_allreduce(XComm* xc, const double* vals, int nr, double* out) {
+    const int world = xc->world, rank = xc->rank;
+    const unsigned long long e = xc->epoch + 1ull;
+    const int par = (int)(e & 1ull);
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < world * nr; t += blockDim.x) {
+        const int q = t / nr, k = t - q * nr;
+        xc->area[q]->buf[par][rank][k] = vals[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        st_release_sys(&xc->area[threadIdx.x]->flag[par][rank], e);
+        if (!spin_until(&xc->area[rank]->flag[par][threadIdx.x], e)) s_ok = 0;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nr) {
+        double x = 0.0;
+        for (int q = 0; q < world; ++q) x += ld_relaxed_sys_f64(&xc->area[rank]->buf[par][q][threadIdx.x]);
+        out[threadIdx.x] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { xc->epoch = e; if (!s_ok) xc->error = 1ull; }
+}
+
 // ---- deterministic grid-wide reduction of NR doubles -------------------------------------------------
 // Every CTA calls this with its per-thread values; the warp/CTA tree and the final pass over the per-CTA
 // partials run in a fixed order, so results are bit-reproducible for a fixed launch configuration.
 // `out[r]` is written by the last CTA to finish.  All threads of the CTA must call it.
+// xc != NULL: the result is additionally summed over all ranks (xcomm_allreduce) by the last CTA.
 template <int NR, int NTHREADS>
 __device__ __forceinline__ void grid_reduce(double (&v)[NR], double* __restrict__ partials,
                                             unsigned int* __restrict__ counter, double* __restrict__ out,
-                                            int cta_linear, int num_ctas) {
+                                            int cta_linear, int num_ctas, XComm* xc = nullptr) {
     __shared__ double s_red[NR][NTHREADS / 32];
+    __shared__ double s_tot[NR];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -119,8 +210,12 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NR], double* __restrict_
             for (int c = lane; c < num_ctas; c += 32) x += __ldcg(&partials[(size_t)c * NR + r]);
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
-            if (lane == 0) out[r] = x;
+            if (lane == 0) { if (xc) s_tot[r] = x; else out[r] = x; }
         }
         if (threadIdx.x == 0) *counter = 0u;
+        if (xc) {                       // block-uniform: s_last and xc are
+            __syncthreads();
+            xcomm_allreduce(xc, s_tot, NR, out);
+        }
     }
 }

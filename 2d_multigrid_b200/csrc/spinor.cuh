@@ -29,6 +29,17 @@ __device__ __forceinline__ Spinor<T> load_spinor_c(const cplx<T>* p, size_t s) {
     }
     return r;
 }
+// system-scope variant for halo rows a strip neighbour wrote over NVLink while this kernel was already running
+template <typename T>
+__device__ __forceinline__ Spinor<T> load_spinor_sys(const cplx<T>* p, size_t s) {
+    Spinor<T> r;
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("ld.volatile.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.c0.x), "=d"(r.c0.y), "=d"(r.c1.x), "=d"(r.c1.y) : "l"(p + 2 * s));
+    } else {
+        asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.c0.x), "=f"(r.c0.y), "=f"(r.c1.x), "=f"(r.c1.y) : "l"(p + 2 * s));
+    }
+    return r;
+}
 template <typename T>
 __device__ __forceinline__ void store_spinor(cplx<T>* __restrict__ p, size_t s, const Spinor<T>& v) {
     if constexpr (sizeof(T) == 8) {

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ST_THREADS)
 stencil_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in, const cplx<T>* __restrict__ in_lo,
                const cplx<T>* __restrict__ in_hi, const cplx<T>* __restrict__ D, const cplx<T>* __restrict__ Dinv,
                const cplx<T>* __restrict__ b, int Lx, int Ly, long long vstride, long long hstride,
-               double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ dots) {
+               double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ dots, XComm* xc) {
     using C = cplx<T>;
     constexpr int G = GroupOf<N>::G;
     constexpr int GPB = ST_THREADS / G;
@@ -127,7 +127,7 @@ stencil_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in, const 
         }
     }
     if (DOTS) grid_reduce<4, ST_THREADS>(red, partials + (size_t)v * MG2D_MAX_PARTIALS * 4, counter + v,
-                                         dots + 4 * v, blockIdx.x, gridDim.x);
+                                         dots + 4 * v, blockIdx.x, gridDim.x, xc);
 }
 
 // red-black Gauss-Seidel half sweep: sites with (x + y + yoff) % 2 == colour are updated in place from the
@@ -238,11 +238,14 @@ stencil_rb_batch_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, cons
 // and no second dependent mat-vec phase (shorter critical path on the small, latency-bound levels).
 // CMODE 0: r = 0 (near-null relaxation); 1: first sweep of a relax call, c = D0^-1 r is computed here and stored in
 // cbuf; 2: c read from cbuf.  NV vectors per pass share one stream of the blocks (blockIdx.y = batch of NV).
-template <typename T, int N, int NV, int CMODE>
+// LINK (strips): boundary rows are processed last; before the first step that touches them the CTA waits for the
+// neighbours' halo rows (flags >= local epoch), every updated boundary value is also stored into the neighbour's halo
+// buffer over NVLink, and the last CTA to finish publishes epoch + 1 (see mg2d_halo_link in include/mg2d.h).
+template <typename T, int N, int NV, int CMODE, bool LINK>
 __global__ void __launch_bounds__(ST_THREADS)
 stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ M,
                      const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, cplx<T>* cbuf, int Lx, int Ly,
-                     int colour, int yoff, long long vstride, long long hstride) {
+                     int colour, int yoff, long long vstride, long long hstride, HaloLinkDev link) {
     using C = cplx<T>;
     constexpr int G = GroupOf<N>::G;
     constexpr int GPB = ST_THREADS / G;
@@ -254,15 +257,34 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
     phi += v0 * vstride; lo += v0 * hstride; hi += v0 * hstride;
     if (CMODE == 1) r += v0 * vstride;
     if (CMODE != 0) cbuf += v0 * vstride;
+    C* push_lo = nullptr; C* push_hi = nullptr;     // neighbours' buffers: next's lo halo <- my last row, prev's hi halo <- my row 0
+    __shared__ unsigned long long s_epoch;
+    bool waited = false;
+    if (LINK) {
+        if (link.push_next_lo) { push_lo = (C*)link.push_next_lo + v0 * hstride; push_hi = (C*)link.push_prev_hi + v0 * hstride; }
+        if (threadIdx.x == 0) s_epoch = link.mine->epoch;
+        __syncthreads();
+    }
     const int Lh = Lx / 2;
     const long long S2 = (long long)Lh * Ly;
     const long long nsteps = (S2 + GPB - 1) / GPB;
+    const long long first_boundary = (Ly >= 2) ? (long long)(Ly - 2) * Lh : 0;      // in the remapped row order
     for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
         long long h = step * GPB + grp;
         const bool active = h < S2;
         if (!active) h = S2 - 1;
-        const int y = (int)(h / Lh);
-        const int x = 2 * (int)(h - (long long)y * Lh) + ((y + yoff + colour) & 1);
+        int y = (int)(h / Lh);
+        const int xh = (int)(h - (long long)y * Lh);
+        if (LINK) {
+            y = (y + 1 == Ly) ? 0 : y + 1;                                         // rows 1 .. Ly-1, then 0
+            if (link.wait && !waited && step * GPB + GPB - 1 >= first_boundary) {   // CTA-uniform
+                if (threadIdx.x == 0 && !(spin_until(&link.mine->flag_lo, s_epoch) && spin_until(&link.mine->flag_hi, s_epoch)))
+                    atomicExch(&link.mine->error, 1ull);
+                __syncthreads();
+                waited = true;
+            }
+        }
+        const int x = 2 * xh + ((y + yoff + colour) & 1);
         const size_t s = (size_t)y * Lx + x;
         const C* Ms = M + s * 4 * N * N;
         C acc[NV];
@@ -277,7 +299,15 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
             const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
             const long long st = (in_hi || in_lo) ? hstride : vstride;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) cfma(acc[v], d, __ldcg(p + (size_t)v * st));
+            for (int v = 0; v < NV; ++v) {
+                C val;
+                if (LINK && (in_hi || in_lo)) {       // peer-written memory: bypass L1
+                    const double2* q = reinterpret_cast<const double2*>(p + (size_t)v * st);
+                    if constexpr (sizeof(T) == 8) { val.x = ld_relaxed_sys_f64(&q->x); val.y = ld_relaxed_sys_f64(&q->y); }
+                    else { const double pk = ld_relaxed_sys_f64(reinterpret_cast<const double*>(p + (size_t)v * st)); val = *reinterpret_cast<const C*>(&pk); }
+                } else val = __ldcg(p + (size_t)v * st);
+                cfma(acc[v], d, val);
+            }
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -291,7 +321,27 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
             } else if (CMODE == 2) {
                 acc[v] = cadd(acc[v], __ldg(cbuf + (size_t)v * vstride + s * N + i));
             }
-            if (active && jp == 0) phi[(size_t)v * vstride + s * N + i] = acc[v];
+            if (active && jp == 0) {
+                phi[(size_t)v * vstride + s * N + i] = acc[v];
+                if (LINK && push_lo) {
+                    if (y == 0) push_hi[(size_t)v * hstride + (size_t)x * N + i] = acc[v];
+                    if (y + 1 == Ly) push_lo[(size_t)v * hstride + (size_t)x * N + i] = acc[v];
+                }
+            }
+        }
+    }
+    if (LINK && push_lo) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
+            if (t == (unsigned long long)gridDim.x * gridDim.y - 1ull) {
+                __threadfence_system();
+                link.mine->ticket = 0ull;
+                st_release_sys(&link.next->flag_lo, s_epoch + 1ull);
+                st_release_sys(&link.prev->flag_hi, s_epoch + 1ull);
+                link.mine->epoch = s_epoch + 1ull;
+            }
         }
     }
 }
@@ -515,7 +565,7 @@ int launch_stencil(mg2d_ctx* ctx, void* out, const void* in, const void* lo, con
     dim3 grid(gx, nvec);
 #define SL(MODE, DOTS)                                                                                         \
     stencil_kernel<T, N, MODE, DOTS><<<grid, ST_THREADS, 0, st>>>((C*)out, (const C*)in, (const C*)lo, (const C*)hi, \
-        (const C*)D, (const C*)Dinv, (const C*)b, Lx, Ly, vstride, hstride, ctx->partials, ctx->counter, dots)
+        (const C*)D, (const C*)Dinv, (const C*)b, Lx, Ly, vstride, hstride, ctx->partials, ctx->counter, dots, (ctx->xreduce && nvec == 1) ? ctx->xcomm : nullptr)
     if (mode == 0) { if (dots) SL(0, true); else SL(0, false); }
     else if (mode == 1) { if (dots) SL(1, true); else SL(1, false); }
     else SL(2, false);
@@ -597,20 +647,33 @@ int dispatch_rb(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* hi,
     }
 }
 
+inline HaloLinkDev make_link(const mg2d_halo_link* l) {
+    HaloLinkDev d;
+    memset(&d, 0, sizeof(d));
+    if (l) {
+        d.mine = (HaloSlot*)l->slot_mine; d.prev = (HaloSlot*)l->slot_prev; d.next = (HaloSlot*)l->slot_next;
+        d.push_next_lo = l->push_next_lo; d.push_prev_hi = l->push_prev_hi; d.wait = l->wait;
+    }
+    return d;
+}
+
 template <typename T, int N>
 int launch_rb_pm(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* M, const void* Dinv, const void* r,
                  void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride, long long hstride,
-                 cudaStream_t st) {
+                 const mg2d_halo_link* link, cudaStream_t st) {
     using C = cplx<T>;
     constexpr int GPB = ST_THREADS / GroupOf<N>::G;
     const long long S2 = (long long)(Lx / 2) * Ly;
     long long nsteps = (S2 + GPB - 1) / GPB;
     long long cap = (long long)ctx->num_sms * 32;
     const int gx = (int)(nsteps < cap ? nsteps : cap);
-#define PM(NV, CM) stencil_rb_pm_kernel<T, N, NV, CM><<<dim3(gx, nvec / NV), ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
-        (const C*)M, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, vstride, hstride)
-    if (N >= 4 && nvec % 4 == 0) { if (cmode == 0) PM(4, 0); else if (cmode == 1) PM(4, 1); else PM(4, 2); }
-    else                         { if (cmode == 0) PM(1, 0); else if (cmode == 1) PM(1, 1); else PM(1, 2); }
+    const HaloLinkDev ld = make_link(link);
+#define PM(NV, CM, LK) stencil_rb_pm_kernel<T, N, NV, CM, LK><<<dim3(gx, nvec / NV), ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
+        (const C*)M, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, vstride, hstride, ld)
+#define PMC(NV, LK) do { if (cmode == 0) PM(NV, 0, LK); else if (cmode == 1) PM(NV, 1, LK); else PM(NV, 2, LK); } while (0)
+    if (N >= 4 && nvec % 4 == 0) { if (link) PMC(4, true); else PMC(4, false); }
+    else                         { if (link) PMC(1, true); else PMC(1, false); }
+#undef PMC
 #undef PM
     return mg2d_check_launch(ctx, "mg2d_relax_rb_pm");
 }
@@ -618,9 +681,9 @@ int launch_rb_pm(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const
 template <typename T>
 int dispatch_rb_pm(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* hi, const void* M, const void* Dinv,
                    const void* r, void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride,
-                   long long hstride, cudaStream_t st) {
+                   long long hstride, const mg2d_halo_link* link, cudaStream_t st) {
     switch (n) {
-#define CASE(N) case N: return launch_rb_pm<T, N>(ctx, phi, lo, hi, M, Dinv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st)
+#define CASE(N) case N: return launch_rb_pm<T, N>(ctx, phi, lo, hi, M, Dinv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st)
         CASE(1); CASE(2); CASE(4); CASE(8); CASE(16); CASE(32);
 #undef CASE
         default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb_pm: n_dof must be one of 1,2,4,8,16,32");
@@ -762,13 +825,14 @@ extern "C" int mg2d_premultiply(mg2d_ctx* ctx, void* M, const void* D, const voi
 
 extern "C" int mg2d_relax_rb_pm(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* M, const void* D0inv,
                                 const void* r, void* cbuf, int cmode, int n, int Lx, int Ly, int colour, int yoff, int dtype,
-                                int nvec, long long vstride, long long hstride, void* stream) {
+                                int nvec, long long vstride, long long hstride, const mg2d_halo_link* link, void* stream) {
     if (!ctx) return MG2D_EINVAL;
     if (!phi || !phi_lo || !phi_hi || !M || Lx < 2 || (Lx & 1) || Ly < 1 || nvec < 1 || (colour != 0 && colour != 1) ||
-        cmode < 0 || cmode > 2 || (cmode == 1 && (!r || !D0inv || !cbuf)) || (cmode == 2 && !cbuf))
+        cmode < 0 || cmode > 2 || (cmode == 1 && (!r || !D0inv || !cbuf)) || (cmode == 2 && !cbuf) ||
+        (link && (!link->slot_mine || !link->slot_prev || !link->slot_next || ((link->push_next_lo == nullptr) != (link->push_prev_hi == nullptr)))))
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm: bad argument (Lx must be even)");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MG2D_C128) return dispatch_rb_pm<double>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
-    if (dtype == MG2D_C64)  return dispatch_rb_pm<float>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, st);
+    if (dtype == MG2D_C128) return dispatch_rb_pm<double>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st);
+    if (dtype == MG2D_C64)  return dispatch_rb_pm<float>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm: bad dtype");
 }

@@ -31,7 +31,7 @@ wilson_march_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in,
                     const cplx<T>* __restrict__ U, const cplx<T>* __restrict__ U_lo,
                     const cplx<T>* __restrict__ b, T diag, int Lx, int Ly, int RY,
                     double* __restrict__ partials, unsigned int* __restrict__ counter,
-                    double* __restrict__ dots) {
+                    double* __restrict__ dots, XComm* xc) {
     using C = cplx<T>;
     const int nsx = (Lx + WX - 1) / WX;
     const int nsy = (Ly + RY - 1) / RY;
@@ -106,7 +106,7 @@ wilson_march_kernel(cplx<T>* __restrict__ out, const cplx<T>* __restrict__ in,
             prev = cur; cur = next; uy_prev = uy;
         }
     }
-    if (DOTS) grid_reduce<4, WX>(red, partials, counter, dots, blockIdx.x, gridDim.x);
+    if (DOTS) grid_reduce<4, WX>(red, partials, counter, dots, blockIdx.x, gridDim.x, xc);
 }
 
 // red-black Gauss-Seidel half sweep, matrix-free: phi(s) = (r(s) - hop(s)) / (2+m) on the sites with
@@ -200,7 +200,7 @@ int launch_wilson(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo, c
     const T diag = (T)(2.0 + mass);
 #define WL(MODE, DOTS)                                                                                      \
     wilson_march_kernel<T, MODE, DOTS><<<grid, WX, 0, st>>>((C*)out, (const C*)in, (const C*)in_lo,          \
-        (const C*)in_hi, (const C*)U, (const C*)U_lo, (const C*)b, diag, Lx, Ly, RY, ctx->partials, ctx->counter, dots)
+        (const C*)in_hi, (const C*)U, (const C*)U_lo, (const C*)b, diag, Lx, Ly, RY, ctx->partials, ctx->counter, dots, ctx->xreduce ? ctx->xcomm : nullptr)
     if (mode == MG2D_MODE_APPLY) { if (dots) WL(0, true); else WL(0, false); }
     else                         { if (dots) WL(1, true); else WL(1, false); }
 #undef WL

@@ -33,6 +33,7 @@ struct Rb2Args {
     const cplx<T>* r; const cplx<T>* r_lo; const cplx<T>* r_hi;
     T inv_diag;
     int Lx, Ly, RY, yoff;
+    HaloLinkDev link;      // strips: fused neighbour push / wait (mine == NULL: none)
 };
 
 template <typename T>
@@ -40,6 +41,15 @@ __device__ __forceinline__ const cplx<T>* rb2_row(const cplx<T>* f, const cplx<T
     if (y < 0) return lo2 + (size_t)(y + 2) * Lx * 2;
     if (y >= Ly) return hi + (size_t)(y - Ly) * Lx * 2;
     return f + (size_t)y * Lx * 2;
+}
+
+// phi of row y, column x: rows outside [0, Ly) come from the halo buffers, which on linked strips a neighbour kernel has
+// just written over NVLink (read them with system-scope loads, never through the non-coherent path)
+template <typename T>
+__device__ __forceinline__ Spinor<T> rb2_phi(const Rb2Args<T>& a, int y, int x, bool linked) {
+    const cplx<T>* row = rb2_row<T>(a.in, a.in_lo2, a.in_hi2, y, a.Lx, a.Ly);
+    if (linked && (y < 0 || y >= a.Ly)) return load_spinor_sys<T>(row, (size_t)x);
+    return load_spinor<T>(row, (size_t)x);
 }
 
 // phi(s) <- (r(s) - 1/2 hop(s)) / (2+m);  a_xp = (psi0 - psi1)(s+x), wb_xm = conj(U_x(s-x)) (psi0 + psi1)(s-x)
@@ -67,7 +77,29 @@ __device__ __forceinline__ Spinor<T> rb2_update(cplx<T> ux, cplx<T> a_xp, cplx<T
     return o;
 }
 
-template <typename T, bool HAS_R>
+// row y of the result: the lane's two columns; boundary rows also go to the strip neighbours' halo buffers
+// (rows 0,1 -> prev's hi2 buffer, rows Ly-2,Ly-1 -> next's lo2 buffer)
+template <typename T>
+__device__ __forceinline__ void rb2_store(const Rb2Args<T>& a, int y, int x0, int x1, bool act0, bool act1, const Spinor<T>& v0,
+                                          const Spinor<T>& v1, cplx<T>* push_lo, cplx<T>* push_hi) {
+    cplx<T>* orow = a.out + (size_t)y * a.Lx * 2;
+    if (act0) store_spinor<T>(orow, (size_t)x0, v0);
+    if (act1) store_spinor<T>(orow, (size_t)x1, v1);
+    if (push_lo) {
+        if (y < 2) {
+            cplx<T>* prow = push_hi + (size_t)y * a.Lx * 2;
+            if (act0) store_spinor<T>(prow, (size_t)x0, v0);
+            if (act1) store_spinor<T>(prow, (size_t)x1, v1);
+        }
+        if (y + 2 >= a.Ly) {
+            cplx<T>* prow = push_lo + (size_t)(y + 2 - a.Ly) * a.Lx * 2;
+            if (act0) store_spinor<T>(prow, (size_t)x0, v0);
+            if (act1) store_spinor<T>(prow, (size_t)x1, v1);
+        }
+    }
+}
+
+template <typename T, bool HAS_R, bool LINKED>
 __global__ void __launch_bounds__(RB2_THREADS, 4)
 wilson_rb2_kernel(Rb2Args<T> a) {
     using C = cplx<T>;
@@ -77,8 +109,21 @@ wilson_rb2_kernel(Rb2Args<T> a) {
     const int nchunks = (Ly + RY - 1) / RY;
     const long long nitems = (long long)ntx * nchunks;
     const long long wstride = (long long)gridDim.x * (RB2_THREADS / 32);
+    // strips: chunks that touch the halo rows come last (order 1, 2, .., nchunks-1, 0), wait for the neighbours' rows
+    // (flags >= local epoch) before their first halo read and store the boundary rows they produce into the
+    // neighbours' two-row halo buffers; the last CTA to finish publishes epoch + 1 (mg2d_halo_link, include/mg2d.h)
+    constexpr bool linked = LINKED;
+    unsigned long long epoch = 0ull;
+    bool waited = false;
+    C* push_lo = nullptr; C* push_hi = nullptr;
+    if (linked) {
+        epoch = a.link.mine->epoch;
+        push_lo = (C*)a.link.push_next_lo; push_hi = (C*)a.link.push_prev_hi;
+    }
     for (long long item = (long long)blockIdx.x * (RB2_THREADS / 32) + (threadIdx.x >> 5); item < nitems; item += wstride) {
-        const int chunk = (int)(item / ntx), tile = (int)(item - (long long)chunk * ntx);
+        int chunk = (int)(item / ntx);
+        const int tile = (int)(item - (long long)chunk * ntx);
+        if (linked) chunk = (chunk + 1 == nchunks) ? 0 : chunk + 1;
         const int X0 = tile * RB2_W;
         const int y0 = chunk * RY, y1 = min(y0 + RY, Ly);
         // the lane's two columns: c0 = X0 + 2*lane - 1 (odd), c1 = X0 + 2*lane (even), periodic
@@ -90,6 +135,12 @@ wilson_rb2_kernel(Rb2Args<T> a) {
         const int xm_out = (x0 == 0) ? Lx - 1 : x0 - 1;            // lane 0: column left of the tile
         const int xp_out = (x1 + 1 == Lx) ? 0 : x1 + 1;            // lane 31: column right of the tile
 
+        if (linked && a.link.wait && !waited && (y0 < 2 || y1 + 2 > Ly)) {           // warp-uniform
+            if (lane == 0 && !(spin_until(&a.link.mine->flag_lo, epoch) && spin_until(&a.link.mine->flag_hi, epoch)))
+                atomicExch(&a.link.mine->error, 1ull);
+            __syncwarp();
+            waited = true;
+        }
         // rho = row of the red stage.  Black column of row y: c0 when (y + yoff) is even (then c1 is red), else c1.
         int rho = y0 - 1;
         Spinor<T> bk_m, bk_0, bk_p, rd_mm, rd_m, rd_0;
@@ -97,8 +148,8 @@ wilson_rb2_kernel(Rb2Args<T> a) {
         C umm_uy0, umm_uy1;                        // U_y of row rho-2
         {
             const bool c1_red_m = ((rho - 1 + 2 + a.yoff) & 1) == 0;     // row rho-1
-            bk_m = load_spinor<T>(rb2_row<T>(a.in, a.in_lo2, a.in_hi2, rho - 1, Lx, Ly), (size_t)(c1_red_m ? x0 : x1));
-            bk_0 = load_spinor<T>(rb2_row<T>(a.in, a.in_lo2, a.in_hi2, rho, Lx, Ly), (size_t)(c1_red_m ? x1 : x0));
+            bk_m = rb2_phi<T>(a, rho - 1, c1_red_m ? x0 : x1, linked);
+            bk_0 = rb2_phi<T>(a, rho, c1_red_m ? x1 : x0, linked);
             const C* ur = rb2_row<T>(a.U, a.U_lo2, a.U_hi, rho - 1, Lx, Ly);
             const Spinor<T> l0 = load_spinor<T>(ur, (size_t)x0), l1 = load_spinor<T>(ur, (size_t)x1);
             um_ux0 = l0.c0; um_uy0 = l0.c1; um_ux1 = l1.c0; um_uy1 = l1.c1;
@@ -107,12 +158,11 @@ wilson_rb2_kernel(Rb2Args<T> a) {
         }
         for (; rho <= y1; ++rho) {
             const bool c1_red = ((rho + 2 + a.yoff) & 1) == 0;          // warp-uniform
-            const C* prow = rb2_row<T>(a.in, a.in_lo2, a.in_hi2, rho, Lx, Ly);
             const C* urow = rb2_row<T>(a.U, a.U_lo2, a.U_hi, rho, Lx, Ly);
             const Spinor<T> l0 = load_spinor<T>(urow, (size_t)x0), l1 = load_spinor<T>(urow, (size_t)x1);
             const C u0_ux0 = l0.c0, u0_uy0 = l0.c1, u0_ux1 = l1.c0, u0_uy1 = l1.c1;
             // black value of row rho+1 sits in the column that is red in row rho
-            bk_p = load_spinor<T>(rb2_row<T>(a.in, a.in_lo2, a.in_hi2, rho + 1, Lx, Ly), (size_t)(c1_red ? x1 : x0));
+            bk_p = rb2_phi<T>(a, rho + 1, c1_red ? x1 : x0, linked);
             const bool do_black = (rho - 1 >= y0);                       // rho - 1 < y1 always
             const C* rrow = HAS_R ? rb2_row<T>(a.r, a.r_lo - (size_t)Lx * 2, a.r_hi, rho, Lx, Ly) : nullptr;
             const C* rrow_m = HAS_R ? rb2_row<T>(a.r, a.r_lo - (size_t)Lx * 2, a.r_hi, rho - 1, Lx, Ly) : nullptr;
@@ -120,7 +170,7 @@ wilson_rb2_kernel(Rb2Args<T> a) {
                 // ---- stage R(rho): target c1; -x source = own c0 (bk_0), +x source = lane+1's c0
                 C a_here = csub(bk_0.c0, bk_0.c1);
                 C a_xp = shfl_c(a_here, lane + 1);
-                if (lane == 31) { const Spinor<T> q = load_spinor<T>(prow, (size_t)xp_out); a_xp = csub(q.c0, q.c1); }
+                if (lane == 31) { const Spinor<T> q = rb2_phi<T>(a, rho, xp_out, linked); a_xp = csub(q.c0, q.c1); }
                 const C wb = cmulc(u0_ux0, cadd(bk_0.c0, bk_0.c1));
                 rd_0 = rb2_update<T, HAS_R>(u0_ux1, a_xp, wb, u0_uy1, bk_p, um_uy1, bk_m, rrow, x1, a.inv_diag);
                 if (do_black) {
@@ -129,16 +179,14 @@ wilson_rb2_kernel(Rb2Args<T> a) {
                     a_xp = shfl_c(a_here, lane + 1);
                     const C wbm = cmulc(um_ux0, cadd(rd_m.c0, rd_m.c1));
                     const Spinor<T> nb = rb2_update<T, HAS_R>(um_ux1, a_xp, wbm, um_uy1, rd_0, umm_uy1, rd_mm, rrow_m, x1, a.inv_diag);
-                    C* orow = a.out + (size_t)(rho - 1) * Lx * 2;
-                    if (act0) store_spinor<T>(orow, (size_t)x0, rd_m);
-                    if (act1) store_spinor<T>(orow, (size_t)x1, nb);
+                    rb2_store<T>(a, rho - 1, x0, x1, act0, act1, rd_m, nb, push_lo, push_hi);
                 }
             } else {
                 // ---- stage R(rho): target c0; +x source = own c1 (bk_0), -x source = lane-1's c1
                 C wb_here = cmulc(u0_ux1, cadd(bk_0.c0, bk_0.c1));
                 C wb_xm = shfl_c(wb_here, lane - 1);
                 if (lane == 0) {
-                    const Spinor<T> q = load_spinor<T>(prow, (size_t)xm_out);
+                    const Spinor<T> q = rb2_phi<T>(a, rho, xm_out, linked);
                     wb_xm = cmulc(__ldg(urow + 2 * (size_t)xm_out), cadd(q.c0, q.c1));
                 }
                 const C ap = csub(bk_0.c0, bk_0.c1);
@@ -149,9 +197,7 @@ wilson_rb2_kernel(Rb2Args<T> a) {
                     wb_xm = shfl_c(wb_here, lane - 1);
                     const C apm = csub(rd_m.c0, rd_m.c1);
                     const Spinor<T> nb = rb2_update<T, HAS_R>(um_ux0, apm, wb_xm, um_uy0, rd_0, umm_uy0, rd_mm, rrow_m, x0, a.inv_diag);
-                    C* orow = a.out + (size_t)(rho - 1) * Lx * 2;
-                    if (act0) store_spinor<T>(orow, (size_t)x0, nb);
-                    if (act1) store_spinor<T>(orow, (size_t)x1, rd_m);
+                    rb2_store<T>(a, rho - 1, x0, x1, act0, act1, nb, rd_m, push_lo, push_hi);
                 }
             }
             bk_m = bk_0; bk_0 = bk_p;
@@ -160,14 +206,33 @@ wilson_rb2_kernel(Rb2Args<T> a) {
             um_ux0 = u0_ux0; um_uy0 = u0_uy0; um_ux1 = u0_ux1; um_uy1 = u0_uy1;
         }
     }
+    if (linked && push_lo) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t = atomicAdd(&a.link.mine->ticket, 1ull);
+            if (t == (unsigned long long)gridDim.x - 1ull) {
+                __threadfence_system();
+                a.link.mine->ticket = 0ull;
+                st_release_sys(&a.link.next->flag_lo, epoch + 1ull);
+                st_release_sys(&a.link.prev->flag_hi, epoch + 1ull);
+                a.link.mine->epoch = epoch + 1ull;
+            }
+        }
+    }
 }
 
 template <typename T>
 int launch_rb2(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo2, const void* in_hi2, const void* U,
                const void* U_lo2, const void* U_hi, const void* r, const void* r_lo, const void* r_hi, double mass,
-               int Lx, int Ly, int yoff, cudaStream_t st) {
+               int Lx, int Ly, int yoff, const mg2d_halo_link* link, cudaStream_t st) {
     using C = cplx<T>;
     Rb2Args<T> a;
+    memset(&a.link, 0, sizeof(a.link));
+    if (link) {
+        a.link.mine = (HaloSlot*)link->slot_mine; a.link.prev = (HaloSlot*)link->slot_prev; a.link.next = (HaloSlot*)link->slot_next;
+        a.link.push_next_lo = link->push_next_lo; a.link.push_prev_hi = link->push_prev_hi; a.link.wait = link->wait;
+    }
     a.out = (C*)out; a.in = (const C*)in; a.in_lo2 = (const C*)in_lo2; a.in_hi2 = (const C*)in_hi2;
     a.U = (const C*)U; a.U_lo2 = (const C*)U_lo2; a.U_hi = (const C*)U_hi;
     a.r = (const C*)r; a.r_lo = (const C*)r_lo; a.r_hi = (const C*)r_hi;
@@ -184,8 +249,13 @@ int launch_rb2(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo2, con
     long long grid = (nitems + RB2_THREADS / 32 - 1) / (RB2_THREADS / 32);
     const long long cap = (long long)ctx->num_sms * 4;
     if (grid > cap) grid = cap;
-    if (r) wilson_rb2_kernel<T, true><<<(int)grid, RB2_THREADS, 0, st>>>(a);
-    else   wilson_rb2_kernel<T, false><<<(int)grid, RB2_THREADS, 0, st>>>(a);
+    if (link) {
+        if (r) wilson_rb2_kernel<T, true, true><<<(int)grid, RB2_THREADS, 0, st>>>(a);
+        else   wilson_rb2_kernel<T, false, true><<<(int)grid, RB2_THREADS, 0, st>>>(a);
+    } else {
+        if (r) wilson_rb2_kernel<T, true, false><<<(int)grid, RB2_THREADS, 0, st>>>(a);
+        else   wilson_rb2_kernel<T, false, false><<<(int)grid, RB2_THREADS, 0, st>>>(a);
+    }
     return mg2d_check_launch(ctx, "mg2d_wilson_relax_rb2");
 }
 
@@ -193,13 +263,15 @@ int launch_rb2(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo2, con
 
 extern "C" int mg2d_wilson_relax_rb2(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo2, const void* in_hi2,
                                      const void* U, const void* U_lo2, const void* U_hi, const void* r, const void* r_lo,
-                                     const void* r_hi, double mass, int Lx, int Ly, int yoff, int dtype, void* stream) {
+                                     const void* r_hi, double mass, int Lx, int Ly, int yoff, int dtype,
+                                     const mg2d_halo_link* link, void* stream) {
     if (!ctx) return MG2D_EINVAL;
-    if (!out || !in || !in_lo2 || !in_hi2 || !U || !U_lo2 || !U_hi || Lx < 2 || (Lx & 1) || Ly < 2 || (r && (!r_lo || !r_hi)))
+    if (!out || !in || !in_lo2 || !in_hi2 || !U || !U_lo2 || !U_hi || Lx < 2 || (Lx & 1) || Ly < 2 || (r && (!r_lo || !r_hi)) ||
+        (link && (!link->slot_mine || !link->slot_prev || !link->slot_next || ((link->push_next_lo == nullptr) != (link->push_prev_hi == nullptr)))))
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_relax_rb2: bad argument (Lx even, Ly >= 2)");
     if (out == in) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_relax_rb2: out must not alias in");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == MG2D_C128) return launch_rb2<double>(ctx, out, in, in_lo2, in_hi2, U, U_lo2, U_hi, r, r_lo, r_hi, mass, Lx, Ly, yoff, st);
-    if (dtype == MG2D_C64)  return launch_rb2<float>(ctx, out, in, in_lo2, in_hi2, U, U_lo2, U_hi, r, r_lo, r_hi, mass, Lx, Ly, yoff, st);
+    if (dtype == MG2D_C128) return launch_rb2<double>(ctx, out, in, in_lo2, in_hi2, U, U_lo2, U_hi, r, r_lo, r_hi, mass, Lx, Ly, yoff, link, st);
+    if (dtype == MG2D_C64)  return launch_rb2<float>(ctx, out, in, in_lo2, in_hi2, U, U_lo2, U_hi, r, r_lo, r_hi, mass, Lx, Ly, yoff, link, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_wilson_relax_rb2: bad dtype");
 }

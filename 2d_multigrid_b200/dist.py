@@ -31,9 +31,13 @@ from .mg import MG
 from .params import MGParams
 
 MIN_ROWS = int(os.environ.get("MG2D_MIN_ROWS", "32"))
-HALO_MODE = os.environ.get("MG2D_HALO", "p2p")      # 'p2p': one fused NVLink kernel per exchange; 'nccl': send/recv
-SLAB_BYTES = int(os.environ.get("MG2D_P2P_SLAB_MB", "192")) << 20
-SLOT_REGION = 1 << 16                                # 1024 slots of 64 bytes at the start of the slab
+HALO_MODE = os.environ.get("MG2D_HALO", "p2p")      # 'p2p': NVLink peer stores from our own kernels; 'nccl': send/recv
+FUSED = os.environ.get("MG2D_FUSED", "1") != "0"    # p2p only: halo push fused into the smoother kernels, reductions
+                                                    # summed over ranks inside the producing kernel
+SLAB_BYTES = int(os.environ.get("MG2D_P2P_SLAB_MB", "256")) << 20
+SLOT_REGION = 1 << 16                                # 1024 halo slots of 64 bytes at the start of the slab
+MAILBOX_OFF = 1 << 16                                # all-reduce mailbox (XRedArea) of the rank
+DATA_OFF = 1 << 20                                   # halo row buffers
 
 
 class _Ptr:
@@ -59,65 +63,128 @@ def plan_strips(p: MGParams, world: int, min_rows: int = MIN_ROWS):
 
 
 class Comm:
-    def __init__(self, world: int, rank: int, group=None):
+    """The ranks of one node as strip neighbours.  With the 'p2p' halo mode every rank owns a CUDA-IPC slab that all
+    peers map: 64-byte halo slots, the all-reduce mailbox and, per exchanged field, two pairs (A/B) of halo row buffers.
+      * exchange_rows: ONE standalone kernel (mg2d_halo_exchange) per exchange, buffers A;
+      * fused_link: the descriptor a smoother kernel takes to push its boundary rows itself (alternating B, A, ...)
+        and to wait for the neighbours' rows in its boundary work only -- no exchange launch between half sweeps;
+      * reductions: summed over the ranks inside the producing kernel (mg2d_comm_reduce) or by mg2d_allreduce.
+    world = 1 (`Comm.single`) makes the rank its own neighbour: the same code paths run on one GPU (tests)."""
+
+    def __init__(self, world: int, rank: int, group=None, backend: str | None = None):
         self.world, self.rank, self.group = world, rank, group
         self.prev, self.next = (rank - 1) % world, (rank + 1) % world
         self._halo = {}
-        self.backend = dist.get_backend(group)
+        self.backend = backend if backend is not None else dist.get_backend(group)
         self.p2p = None            # set by enable_p2p()
+        self.fused = False
+        self.xdesc = None
 
-    # ---- peer-to-peer path: CUDA-IPC slab + one fused exchange kernel (mg2d_halo_exchange) --------------------
+    @classmethod
+    def single(cls, ctx, device, slab_bytes: int = 64 << 20):
+        """One rank that is its own strip neighbour (periodic wrap through the halo machinery)."""
+        c = cls(1, 0, backend="self")
+        c.enable_p2p(ctx, device, slab_bytes)
+        return c
+
+    # ---- peer-to-peer path: CUDA-IPC slabs ---------------------------------------------------------------------
     def enable_p2p(self, ctx, device, slab_bytes: int = SLAB_BYTES):
-        """Allocate this rank's slab, trade IPC handles, map the two neighbours' slabs."""
+        """Allocate this rank's slab, trade IPC handles, map every peer's slab, build the reduction descriptor."""
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         ctx.call("mg2d_ipc_alloc", slab_bytes, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
-        allh = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(allh, mine, group=self.group)
         base = {self.rank: ptr.value}
-        for peer in {self.prev, self.next} - {self.rank}:
-            hb = (ctypes.c_ubyte * 64)(*allh[peer].cpu().tolist())
-            pp = ctypes.c_void_p()
-            ctx.call("mg2d_ipc_open", ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(pp))
-            base[peer] = pp.value
-        dist.barrier(group=self.group)
-        self.p2p = {"ctx": ctx, "base": base, "slots": 0, "off": SLOT_REGION, "size": slab_bytes, "keys": {}}
+        if self.world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=self.group)
+            for peer in range(self.world):
+                if peer == self.rank:
+                    continue
+                hb = (ctypes.c_ubyte * 64)(*allh[peer].cpu().tolist())
+                pp = ctypes.c_void_p()
+                ctx.call("mg2d_ipc_open", ctypes.cast(hb, ctypes.c_void_p), ctypes.byref(pp))
+                base[peer] = pp.value
+            dist.barrier(group=self.group)
+        self.p2p = {"ctx": ctx, "base": base, "slots": 0, "off": DATA_OFF, "size": slab_bytes, "keys": {}}
+        if self.world <= 8:
+            boxes = (ctypes.c_void_p * self.world)(*[base[q] + MAILBOX_OFF for q in range(self.world)])
+            desc = ctypes.c_void_p()
+            ctx.call("mg2d_comm_create", self.world, self.rank, boxes, ctypes.byref(desc))
+            self.xdesc = desc.value
+            self.fused = FUSED
+
+    def attach(self, ctx):
+        """Let another handle of this rank (the complex64 shadow hierarchy) use the same reduction descriptor."""
+        if self.xdesc is not None:
+            ctx.call("mg2d_comm_attach", self.xdesc)
+
+    def _entry(self, key, nvec: int, row: int):
+        """Slot + halo row buffers (lo/hi x A/B) of one exchanged field; identical offsets on every rank."""
+        st = self.p2p
+        k = (key, nvec, row)
+        if k not in st["keys"]:
+            need = ((nvec * row + 255) // 256) * 256
+            if st["off"] + 4 * need > st["size"] or (st["slots"] + 1) * 64 > SLOT_REGION:
+                raise MemoryError("P2P halo slab exhausted: raise MG2D_P2P_SLAB_MB")
+            o = st["off"]
+            st["keys"][k] = {"slot": st["slots"] * 64, "lo": (o, o + 2 * need), "hi": (o + need, o + 3 * need)}
+            st["slots"] += 1
+            st["off"] += 4 * need
+        return st["keys"][k]
 
     def _p2p_exchange(self, t, Lx, Ly, width, nvec, key, depth=1):
         from .mg import _stream
         st = self.p2p
         es = t.element_size()
         row = Lx * width * es * depth         # `depth` boundary rows are one contiguous piece
-        k = (key, nvec, row)
-        if k not in st["keys"]:
-            need = ((nvec * row + 255) // 256) * 256
-            if st["off"] + 2 * need > st["size"] or (st["slots"] + 1) * 64 > SLOT_REGION:
-                raise MemoryError("P2P halo slab exhausted: raise MG2D_P2P_SLAB_MB")
-            st["keys"][k] = (st["slots"] * 64, st["off"], st["off"] + need)
-            st["slots"] += 1
-            st["off"] += 2 * need
-        slot, lo_off, hi_off = st["keys"][k]
+        e = self._entry(key, nvec, row)
         b = st["base"]
         me, pv, nx = b[self.rank], b[self.prev], b[self.next]
         stride = Ly * Lx * width * es
         st["ctx"].call("mg2d_halo_exchange", t.data_ptr(), t.data_ptr() + stride - row, stride, row, nvec,
-                       nx + lo_off, pv + hi_off, me + slot, pv + slot, nx + slot, _stream())
-        return _Ptr(me + lo_off), _Ptr(me + hi_off)
+                       nx + e["lo"][0], pv + e["hi"][0], me + e["slot"], pv + e["slot"], nx + e["slot"], _stream())
+        return _Ptr(me + e["lo"][0]), _Ptr(me + e["hi"][0])
 
-    def p2p_errors(self, device) -> int:
+    def fused_link(self, t, Lx, Ly, width, nvec, key, depth: int, phase: int, push: bool):
+        """For the phase-th kernel after a standalone exchange of the same field (phase 0 reads buffers A):
+        returns (mg2d_halo_link, lo pointer, hi pointer).  The kernel reads its halos from buffers phase % 2 and, when
+        `push`, stores its boundary rows into the neighbours' buffers (phase + 1) % 2."""
+        from ._lib import HaloLink
+        st = self.p2p
+        row = Lx * width * t.element_size() * depth
+        e = self._entry(key, nvec, row)
+        b = st["base"]
+        me, pv, nx = b[self.rank], b[self.prev], b[self.next]
+        rd, wr = phase & 1, (phase + 1) & 1
+        link = HaloLink(me + e["slot"], pv + e["slot"], nx + e["slot"],
+                        (nx + e["lo"][wr]) if push else None, (pv + e["hi"][wr]) if push else None, 1)
+        return link, me + e["lo"][rd], me + e["hi"][rd]
+
+    def check_errors(self):
+        """Raise if any exchange / reduction of this rank timed out waiting for a peer (synchronises)."""
+        if self.p2p is None:
+            return
+        from ._lib import MG2DError
+        st = self.p2p
+        n = ctypes.c_longlong(0)
+        torch.cuda.synchronize()
+        st["ctx"].call("mg2d_halo_errors", st["base"][self.rank], st["slots"], ctypes.byref(n))
+        m = ctypes.c_longlong(0)
+        if self.xdesc is not None:
+            st["ctx"].call("mg2d_comm_error", self.xdesc, ctypes.byref(m))
+        if n.value or m.value:
+            raise MG2DError(f"rank {self.rank}: {n.value} halo exchange(s) / {m.value} reduction(s) timed out waiting for a peer; "
+                            "the fields of this solve are not valid")
+
+    def p2p_errors(self, device=None) -> int:
         """Number of exchanges that timed out waiting for a neighbour (0 = healthy)."""
         if self.p2p is None:
             return 0
-        n = self.p2p["slots"]
-        if n == 0:
-            return 0
-        buf = (ctypes.c_ulonglong * (8 * n))()
+        n = ctypes.c_longlong(0)
         torch.cuda.synchronize()
-        import ctypes as C
-        cudart = C.CDLL("libcudart.so.12")
-        cudart.cudaMemcpy(buf, C.c_void_p(self.p2p["base"][self.rank]), C.c_size_t(64 * n), C.c_int(2))
-        return int(sum(buf[8 * i + 5] for i in range(n)))
+        self.p2p["ctx"].call("mg2d_halo_errors", self.p2p["base"][self.rank], self.p2p["slots"], ctypes.byref(n))
+        return int(n.value)
 
     def exchange_rows(self, t: torch.Tensor, Lx: int, Ly: int, width: int, nvec: int = 1, key=None, as_tensor: bool = False,
                       depth: int = 1):
@@ -133,7 +200,9 @@ class Comm:
         if k not in self._halo:
             self._halo[k] = (torch.empty_like(first), torch.empty_like(first))
         lo, hi = self._halo[k]
-        if self.backend == "nccl":
+        if self.world == 1:
+            lo.copy_(last); hi.copy_(first)
+        elif self.backend == "nccl":
             # order matters when prev == next (2 ranks): my last row is the peer's lo, my first row its hi
             ops = [dist.P2POp(dist.isend, last, self.next, self.group), dist.P2POp(dist.isend, first, self.prev, self.group),
                    dist.P2POp(dist.irecv, lo, self.prev, self.group), dist.P2POp(dist.irecv, hi, self.next, self.group)]
@@ -147,12 +216,22 @@ class Comm:
         return lo, hi
 
     def allreduce(self, t: torch.Tensor, op: str = "sum"):
+        if self.world == 1:
+            return
+        if (self.fused and op == "sum" and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= 64):
+            from .mg import _stream
+            self.p2p["ctx"].call("mg2d_allreduce", t.data_ptr(), t.numel(), _stream())     # our own mailbox kernel
+            return
         dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
 
     def allgather(self, full: torch.Tensor, strip: torch.Tensor):
         """full = concatenation of every rank's strip in rank order (strips are contiguous row blocks)."""
-        dist.all_gather_into_tensor(full.reshape(-1), strip.reshape(-1).contiguous(), group=self.group) \
-            if self.backend == "nccl" else self._allgather_list(full, strip)
+        if self.world == 1:
+            full.reshape(-1).copy_(strip.reshape(-1))
+        elif self.backend == "nccl":
+            dist.all_gather_into_tensor(full.reshape(-1), strip.reshape(-1).contiguous(), group=self.group)
+        else:
+            self._allgather_list(full, strip)
 
     def _allgather_list(self, full, strip):
         parts = [torch.empty_like(strip) for _ in range(self.world)]
@@ -163,13 +242,13 @@ class Comm:
 class DistMG(MG):
     """MG whose finest levels are strip-decomposed over the ranks of `comm` (see module docstring)."""
 
-    def __init__(self, params: MGParams, comm: Comm, device: int | None = None, min_rows: int = MIN_ROWS):
+    def __init__(self, params: MGParams, comm: Comm, device: int | None = None, min_rows: int = MIN_ROWS, plan=None):
         super().__init__(params, device)
         self.comm = comm
         self.min_rows = min_rows
         if params.ntl:
             raise NotImplementedError("the non-telescoping cycle shifts aggregates across strip boundaries: one GPU only")
-        self.plan = plan_strips(params, comm.world, min_rows)
+        self.plan = plan_strips(params, comm.world, min_rows) if plan is None else plan
         if not self.plan[0][0]:
             raise ValueError(f"lattice {params.L} cannot be cut into {comm.world} strips of >= {min_rows} rows in whole aggregates")
         for lv, (d, rows) in zip(self.LVL, self.plan):
@@ -177,6 +256,7 @@ class DistMG(MG):
                 lv.set_strip(comm.rank * rows, rows)
         if HALO_MODE == "p2p" and comm.p2p is None and comm.backend == "nccl" and comm.world > 1:
             comm.enable_p2p(self.ctx, self.device)
+        comm.attach(self.ctx)
 
     # field movement between a full host/device field and the strips
     def scatter_field(self, full: torch.Tensor) -> torch.Tensor:
@@ -205,10 +285,10 @@ def bcast_float(comm: Comm, v: float, src: int = 0) -> float:
     return float(t.item())
 
 
-def setup(U, params: MGParams, comm: Comm, init_fields: str = "device", null_vectors=None) -> DistMG:
+def setup(U, params: MGParams, comm: Comm, init_fields: str = "device", null_vectors=None, min_rows: int = MIN_ROWS) -> DistMG:
     """Distributed counterpart of the package-level setup(): U is the full link field (every rank keeps its rows)."""
     from .mg import compute_near_null
-    mg = DistMG(params, comm)
+    mg = DistMG(params, comm, min_rows=min_rows)
     if init_fields == "device":
         mg.init_fields()
     else:

@@ -14,6 +14,7 @@ operator D [S, 5, n, n] with COLUMN-major n x n blocks, i.e. D[s, k, j, i] = D_r
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -38,6 +39,24 @@ def _stream():
 def D_to_reference_layout(D: torch.Tensor) -> torch.Tensor:
     """[S,5,j,i] (device layout) <-> [S,5,i,j] (D(s,k)(i,j) of the reference).  Involution."""
     return D.transpose(-1, -2).contiguous()
+
+
+class _GlobalSums:
+    def __init__(self, lv, t, fusable):
+        self.lv, self.t = lv, t
+        self.fuse = bool(lv.distributed and fusable and lv.mg.comm is not None and lv.mg.comm.fused)
+
+    def __enter__(self):
+        if self.fuse:
+            self.lv.mg.ctx.call("mg2d_comm_reduce", 1)
+        return self
+
+    def __exit__(self, *exc):
+        if self.fuse:
+            self.lv.mg.ctx.call("mg2d_comm_reduce", 0)
+        elif exc[0] is None:
+            self.lv.allreduce(self.t)
+        return False
 
 
 class Level:
@@ -104,6 +123,12 @@ class Level:
     def allreduce(self, t, op: str = "sum"):
         if self.distributed:
             self.mg.comm.allreduce(t, op)
+
+    def global_sums(self, t, fusable: bool = True):
+        """Context for kernels that write partial sums into `t`: on a distributed level the sums are made global either
+        inside the kernel itself (mg2d_comm_reduce: the last CTA exchanges with all ranks over NVLink) or, when the kernel
+        cannot (batched reductions) or the comm has no peer mailboxes, by an all-reduce of `t` afterwards."""
+        return _GlobalSums(self, t, fusable)
 
     def init_level(self, gen: StdMT19937 | None):
         """f_init_level (S6/level.h:42-53): phi, r, phi_null drawn in this order (gen None -> ones, rand=0)."""
@@ -185,8 +210,8 @@ class Level:
         """Launch the fused residual + norms of f_get_residue_mag; returns the device dots tensor
         ([0] = |r - D phi|^2, [3] = |r|^2).  No host sync."""
         d = self.dots("resmag")
-        self._stencil(self.work("rtemp"), self.phi, self.r, _lib.MODE_RESID, d)
-        self.allreduce(d[:4])
+        with self.global_sums(d[:4]):
+            self._stencil(self.work("rtemp"), self.phi, self.r, _lib.MODE_RESID, d)
         return d
 
     def get_residue_mag(self) -> float:
@@ -256,22 +281,33 @@ class Level:
             b = r if r is not None else self.work("zero_rhs", key)
             self._stencil(res, phi, b, _lib.MODE_RESID, None, nvec)
             for _ in range(num_iter):
-                self._stencil(t, res, None, _lib.MODE_APPLY, d, nvec)
-                self.allreduce(d[:4 * nvec])
+                with self.global_sums(d[:4 * nvec], fusable=(nvec == 1)):
+                    self._stencil(t, res, None, _lib.MODE_APPLY, d, nvec)
                 mg.ctx.call("mg2d_mr_update", _ptr(phi), _ptr(res), _ptr(t), _ptr(d), float(mg.p.mr_omega),
                             vs, mg.dcode, nvec, vs, _stream())
         elif smoother == "rbgs" and self.matrix_free and mg.two_colour and self.Ly >= 2:
             # both colours per pass, out of place (mg2d_wilson_relax_rb2): ping-pong between phi and a work buffer
             tmp = self.work("rb2_tmp", None if nvec == 1 else nvec)
+            fused = self.distributed and mg.comm.fused
             for v in range(nvec):
                 cur, nxt = (phi, tmp) if nvec == 1 else (phi[v], tmp[v])
                 rv = None if r is None else (r if nvec == 1 else r[v])
                 r_lo, r_hi = (None, None) if rv is None else self._halo(rv)
-                for _ in range(num_iter):
-                    lo2, hi2 = self._halo(cur, depth=2)
+                for it in range(num_iter):
+                    link = None
+                    if fused:
+                        # one standalone exchange in front; afterwards every sweep pushes the two boundary rows it
+                        # produces into the neighbours' (alternating) halo buffers itself and waits only in its boundary chunks
+                        if it == 0:
+                            self._halo(cur, depth=2)
+                        lk, lo2, hi2 = mg.comm.fused_link(cur, self.L, self.Ly, self.n, 1, (self.lvl, self.n, 1, 2), 2, it,
+                                                          push=(it < num_iter - 1))
+                        link = ctypes.byref(lk)
+                    else:
+                        lo2, hi2 = self._halo(cur, depth=2)
                     mg.ctx.call("mg2d_wilson_relax_rb2", _ptr(nxt), _ptr(cur), lo2, hi2, _ptr(self.U), self.U_lo2_ptr,
                                 self.U_hi_ptr, _ptr(rv), r_lo, r_hi, float(mg.p.mass), self.L, self.Ly, self.y0 & 1,
-                                mg.dcode, _stream())
+                                mg.dcode, link, _stream())
                     cur, nxt = nxt, cur
                 if num_iter & 1:
                     mg.ctx.call("mg2d_copy", _ptr(nxt), _ptr(cur), vs, mg.dcode, _stream())
@@ -295,9 +331,18 @@ class Level:
                         self._ensure_M()
                         cmode = 0 if r is None else (1 if it == 0 else 2)
                         cbuf = None if r is None else self.work("pm_c", None if nvec == 1 else nvec)
-                        lo, hi = self._halo(phi, nvec)
+                        link = None
+                        if self.distributed and mg.comm.fused:
+                            k = 2 * it + colour        # one standalone exchange, then the half sweeps push / wait themselves
+                            if k == 0:
+                                self._halo(phi, nvec)
+                            lk, lo, hi = mg.comm.fused_link(phi, self.L, self.Ly, self.n, nvec, (self.lvl, self.n, nvec, 1), 1, k,
+                                                            push=(k < 2 * num_iter - 1))
+                            link = ctypes.byref(lk)
+                        else:
+                            lo, hi = self._halo(phi, nvec)
                         mg.ctx.call("mg2d_relax_rb_pm", _ptr(phi), lo, hi, _ptr(self.M), _ptr(self.D0inv), _ptr(r), _ptr(cbuf),
-                                    cmode, self.n, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, nvec, vs, hs, _stream())
+                                    cmode, self.n, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, nvec, vs, hs, link, _stream())
                     else:
                         self._ensure_D0inv()
                         lo, hi = self._halo(phi, nvec)
@@ -326,9 +371,9 @@ class Level:
             self.matrix_free = True
         for _ in range(num):
             self.relax(p.null_chunk, phi=V, r=None)
-            for v in range(nvec):
-                mg.ctx.call("mg2d_norm2", _ptr(V[v]), vs, mg.dcode, _ptr(nrm[v:]), _stream())
-            self.allreduce(nrm[:nvec])
+            with self.global_sums(nrm[:nvec]):
+                for v in range(nvec):
+                    mg.ctx.call("mg2d_norm2", _ptr(V[v]), vs, mg.dcode, _ptr(nrm[v:]), _stream())
             for v in range(nvec):
                 mg.ctx.call("mg2d_scale_inv_norm", _ptr(V[v]), _ptr(nrm[v:]), vs, mg.dcode, _stream())
         self.matrix_free = stored
@@ -453,12 +498,18 @@ class MG:
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
         self.min_rows = 0
         self.graph_launches = 0    # kernels executed through CUDA-graph replays (not seen by ctx.launches)
+        self.capture_launches = 0  # launches recorded (not executed) while capturing iteration graphs
+
+    def _ctxs(self):
+        """The handles whose launch counters a solve on this hierarchy advances (its own + the complex64 shadow's)."""
+        sh = self.info.get("single")
+        return [self.ctx] + ([sh.ctx] if isinstance(sh, MG) else [])
 
     @property
     def launches(self) -> int:
         """Kernels of libmg2d_sm100.so launched so far (eager + replayed from graphs, minus capture-only)."""
-        cap = sum(g.nlaunch for g in self.info.values() if isinstance(g, CycleGraph))
-        return self.ctx.launches - cap + self.graph_launches
+        cap = sum(g.nlaunch for g in self.info.values() if isinstance(g, CycleGraph)) + self.capture_launches
+        return sum(c.launches for c in self._ctxs()) - cap + self.graph_launches
 
     def _ntl_fields(self, level: int):
         """The phi of NTL[level][0..3] live in one [4,S,n] buffer so that the Gram matrix is one batched launch."""
@@ -537,7 +588,7 @@ def make_single_precision(mg: "MG") -> "MG":
     p32 = dataclasses.replace(mg.p, dtype="complex64", size=[], n_dof=[])
     if mg.comm is not None:
         from .dist import DistMG
-        m32 = DistMG(p32, mg.comm, min_rows=mg.min_rows)
+        m32 = DistMG(p32, mg.comm, min_rows=mg.min_rows, plan=mg.plan)
     else:
         m32 = MG(p32, mg.device_index)
     c64 = torch.complex64
@@ -786,7 +837,17 @@ class CycleGraph:
 
 
 def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, check_every: int = 1,
-               record_phi: bool = False, use_graph: bool = False):
+               record_phi: bool = False, use_graph: bool = False, on_iteration=None):
+    """f_perform_MG; see _perform_MG.  On strips a peer time-out during the solve raises instead of returning fields
+    computed from stale halo rows."""
+    info = _perform_MG(mg, tol, max_iters, check_every, record_phi, use_graph, on_iteration)
+    if mg.comm is not None:
+        mg.comm.check_errors()
+    return info
+
+
+def _perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, check_every: int = 1,
+                record_phi: bool = False, use_graph: bool = False, on_iteration=None):
     """f_perform_MG (S6/modules_main.h:442-481): cycles until |r - D phi|/|r| < tol; diverged if > 1e6.
     The residual norms are produced on the device by the fused residual kernel; the host reads them every
     `check_every` cycles (1 = the reference's behaviour)."""
@@ -808,6 +869,8 @@ def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, c
         for k in range(nb):
             if record_phi:
                 info["phi_hist"].append(mg.LVL[0].phi.clone())
+            if on_iteration is not None:
+                on_iteration(it + k, mg)          # the reference's per-iteration writers (S6/modules_main.h:446-458)
             if cyc is not None:
                 cyc.run()
                 if ntl:
@@ -840,80 +903,128 @@ def perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, c
     return info
 
 
+class IterGraph:
+    """One whole outer iteration (cycle + operator apply + the three fused GCR passes, every reduction on the device)
+    captured into a CUDA graph: one host launch per iteration.  There is one graph per number of stored directions
+    (`slot`), because the stored vectors the iteration reads and the buffers it writes depend on it."""
+
+    def __init__(self, body, state):
+        self.body, self.state, self.graph, self.nlaunch = body, state, None, 0
+
+    def run(self, mg: "MG", slot: int):
+        if self.graph is None:
+            saved = [t.clone() for t in self.state]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):          # warm-up: allocates every lazily created work buffer
+                self.body(slot)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for t, c in zip(self.state, saved):
+                t.copy_(c)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = sum(c.launches for c in mg._ctxs())
+            with torch.cuda.graph(self.graph):
+                self.body(slot)
+            self.nlaunch = sum(c.launches for c in mg._ctxs()) - n0
+            for t, c in zip(self.state, saved):
+                t.copy_(c)
+            mg.capture_launches += self.nlaunch
+        self.graph.replay()
+        mg.graph_launches += self.nlaunch
+
+
 def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, restart: int = 8, check_every: int = 1,
            use_graph: bool = False, precond: "MG | None" = None):
     """Flexible GCR(restart) around one multigrid cycle as preconditioner (mirrors oracle gcr_MG; the reference
     itself only iterates the cycle stationarily).  On entry LVL[0].phi / LVL[0].r hold x0 / b; on exit the
-    solution is in LVL[0].phi.  All scalars (Gram-Schmidt coefficients, step lengths) stay on the device."""
+    solution is in LVL[0].phi.  All scalars (Gram-Schmidt coefficients, step lengths, residual norms; on strips their
+    sums over the ranks) stay on the device; the host reads |r|^2 after every `check_every` iterations (1: no cycle is
+    executed past convergence).  use_graph: each iteration is ONE graph launch (IterGraph)."""
     p = mg.p
     tol = p.tol if tol is None else tol
     max_iters = p.max_iters if max_iters is None else max_iters
+    if restart > 8 or restart < 1:
+        raise ValueError("1 <= restart <= 8 (mg2d_gcr_dots / mg2d_gcr_ortho handle up to 8 stored directions)")
+    check_every = max(1, min(check_every, restart))
     lv0 = mg.LVL[0]
     vs = lv0.S * lv0.n
     call, dc, st = mg.ctx.call, mg.dcode, _stream
     x, b = lv0.work("gcr_x"), lv0.work("gcr_b")
     r = lv0.work("gcr_r")
     Z, W = lv0.work("gcr_Z", restart), lv0.work("gcr_W", restart)
-    if restart > 8:
-        raise ValueError("restart <= 8 (mg2d_gcr_dots / mg2d_gcr_ortho handle up to 8 stored directions)")
-    sc = lv0.dots("gcr")            # [0:4] |w|^2,<w,r> ; [4] |r|^2 ; [5] |b|^2 ; [16:32] <W_j,w> ; [40+j] |w_j|^2
+    sc = lv0.dots("gcr")            # [0:4] |w|^2,<w,r> ; [4] |r|^2 ; [5] |b|^2 ; [16:32] <W_j,w> ; [40+j] |w_j|^2 ; [48+j] |r|^2 after slot j
     call("mg2d_copy", _ptr(x), _ptr(lv0.phi), vs, dc, st())
     call("mg2d_copy", _ptr(b), _ptr(lv0.r), vs, dc, st())
     lv0._stencil(r, x, b, _lib.MODE_RESID, None)
-    call("mg2d_norm2", _ptr(b), vs, dc, _ptr(sc[5:]), st())
-    mg.allreduce(sc[5:6])
+    with lv0.global_sums(sc[5:6]):
+        call("mg2d_norm2", _ptr(b), vs, dc, _ptr(sc[5:]), st())
     pm = mg if precond is None else precond      # hierarchy that runs the cycle (may be the complex64 shadow)
     pl0 = pm.LVL[0]
     for lv in pm.LVL[1:]:
         pm.ctx.call("mg2d_zero", _ptr(lv.phi), lv.S * lv.n, pm.dcode, st())
-    cyc = None
-    if use_graph:
-        gkey = "precond_graph_half" if pm.use_half else "precond_graph"
-        cyc = pm.info.get(gkey)
-        if cyc is None:
-            cyc = pm.info[gkey] = CycleGraph(pm, with_resmag=False, zero_start=True)
     ntl = p.ntl and p.nlevels > 0
-    info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
-    hist = torch.zeros(max(check_every, 1), dtype=torch.float64, device=mg.device)
-    bn2 = None
-    it, slot = 0, 0
-    done = False
     fresh_top = p.nlevels > 0 and pm.p.pre[0] == 0 and pl0.phi_null_c is not None and not ntl
-    while it < max_iters and not done:
-        nb = min(check_every, max_iters - it)
-        for k in range(nb):
-            # z = M(r): the cycle works on (LVL[0].phi, LVL[0].r) of the preconditioner hierarchy, from phi = 0
+    alias = pm is mg and not ntl     # the cycle reads the GCR residual as its right-hand side and writes z in place
+
+    def body(slot):
+        z, w = Z[slot], W[slot]
+        # z = M(r): one cycle from phi = 0 on the preconditioner hierarchy
+        if alias:
+            keep = (pl0.phi, pl0.r)
+            pl0.phi, pl0.r = z, r
+        else:
+            pm.ctx.call("mg2d_convert", _ptr(pl0.r), pm.dcode, _ptr(r), dc, vs, st())
+        try:
             if not fresh_top:      # (with no pre-smoothing the first write to phi is the overwriting prolongation)
                 pm.ctx.call("mg2d_zero", _ptr(pl0.phi), vs, pm.dcode, st())
-            pm.ctx.call("mg2d_convert", _ptr(pl0.r), pm.dcode, _ptr(r), dc, vs, st())
-            if cyc is not None:
-                cyc.run()
-            elif ntl:
+            if ntl:
                 MG_ntl(pm)
             else:
                 MG_simple(pm, zero_start=True)
-            z, w = Z[slot], W[slot]
+        finally:
+            if alias:
+                pl0.phi, pl0.r = keep
+        if not alias:
             pm.ctx.call("mg2d_convert", _ptr(z), dc, _ptr(pl0.phi), pm.dcode, vs, st())
-            lv0._stencil(w, z, None, _lib.MODE_APPLY, None)
-            # classical Gram-Schmidt against the stored directions, then the minimal-residual step (3 fused passes)
-            if slot > 0:
+        lv0._stencil(w, z, None, _lib.MODE_APPLY, None)
+        # classical Gram-Schmidt against the stored directions, then the minimal-residual step (3 fused passes)
+        if slot > 0:
+            with lv0.global_sums(sc[16:16 + 2 * slot]):
                 call("mg2d_gcr_dots", _ptr(W), vs, slot, _ptr(w), vs, dc, _ptr(sc[16:]), st())
-                mg.allreduce(sc[16:16 + 2 * slot])
+        with lv0.global_sums(sc[0:4]):
             call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(r), _ptr(W), _ptr(Z), vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
                  vs, dc, _ptr(sc[0:]), st())
-            mg.allreduce(sc[0:4])
-            sc[40 + slot:41 + slot].copy_(sc[0:1])                       # |w_slot|^2 for later projections
-            call("mg2d_gcr_step", _ptr(x), _ptr(r), _ptr(z), _ptr(w), _ptr(sc[0:]), vs, dc, _ptr(sc[4:]), st())
-            mg.allreduce(sc[4:5])
-            hist[k:k + 1].copy_(sc[4:5])
-            slot += 1
-            if slot >= restart:
-                slot = 0
-        h = hist[:nb].cpu()
+        with lv0.global_sums(sc[48 + slot:49 + slot]):
+            call("mg2d_gcr_step", _ptr(x), _ptr(r), _ptr(z), _ptr(w), _ptr(sc[0:]), _ptr(sc[40 + slot:]), vs, dc,
+                 _ptr(sc[48 + slot:]), st())
+
+    graphs = None
+    if use_graph and pm.p.smoother != "gs":
+        gkey = ("iter_graphs", id(pm), pm.use_half, restart, tuple(pm.p.pre), tuple(pm.p.post))
+        graphs = mg.info.setdefault(gkey, {})
+    info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
+    bn2 = None
+    it, slot = 0, 0
+    done = False
+    while it < max_iters and not done:
+        nb = min(check_every, max_iters - it, restart - slot)
+        slots = []
+        for k in range(nb):
+            if graphs is not None:
+                g = graphs.get(slot)
+                if g is None:
+                    g = graphs[slot] = IterGraph(body, [x, r, sc])
+                g.run(mg, slot)
+            else:
+                body(slot)
+            slots.append(slot)
+            slot = (slot + 1) % restart
+        h = sc[48:56].cpu()
         if bn2 is None:
             bn2 = float(sc[5].item())
-        for k in range(nb):
-            resmag = math.sqrt(h[k].item()) / math.sqrt(bn2) if bn2 > 0 else float("nan")
+        for k, sl in enumerate(slots):
+            resmag = math.sqrt(h[sl].item()) / math.sqrt(bn2) if bn2 > 0 else float("nan")
             info["resnorms"].append(resmag)
             info["iters"] = it + k + 1
             if resmag < tol:
@@ -921,7 +1032,10 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
             if resmag > 1e6 or math.isnan(resmag):
                 info["diverged"] = True; done = True; break
         it += nb
+    info["executed_iters"] = it
     call("mg2d_copy", _ptr(lv0.phi), _ptr(x), vs, dc, st())
     call("mg2d_copy", _ptr(lv0.r), _ptr(b), vs, dc, st())
     info["true_resnorm"] = lv0.get_residue_mag()
+    if mg.comm is not None:
+        mg.comm.check_errors()
     return info

@@ -16,16 +16,21 @@ smoother (no pre-smoothing; 4 / 2 / 8 / 8 ... post-smoothing sweeps on levels 0 
 flexible GCR(8) outer iteration,
 complex128.
 
-Reference arm / cpu_baseline: the reference (single-threaded C++/Eigen) cannot be built for this workload --
-Eigen is absent and its coarse dof count is hard-wired to 4 -- so the CPU side is the oracle PORT running the SAME
-algorithm on a bounded sample: the hierarchy of a 256^2 lattice of the same shape is set up by the numpy oracle (not
-timed), full solves are run by the plain C + OpenMP restatement of the solve loop (oracle/c_port, all host threads) and
-the cost is scaled per site and per iteration to the workload; the JSON says so in `sample`.  The reference's own
-binary IS timed on the configuration it can run (BASELINE configs[1], key `config2_vs_reference_binary`).
+Reference arm / cpu_baseline: the reference (single-threaded C++/Eigen) cannot be built for this workload -- Eigen is
+absent and its coarse dof count is hard-wired to 4 -- so the CPU side is the oracle PORT running the SAME algorithm: full
+solves (to 1e-10, with the iteration count the CPU solve itself needs) by the plain C + OpenMP restatement of the solve
+loop (oracle/c_port) with an explicitly set thread count (every host processor; launchers export OMP_NUM_THREADS=1).
+  * `--impl reference` (no GPU code on the path): hierarchy of a 512^2 lattice of the workload's shape set up by the numpy
+    oracle (not timed); `value` = measured solve time x (L/512)^2 sites, `ms_per_step` = the measured wall time of a step.
+  * `cpu_baseline` of the GPU arm (rank 0, N=1): the hierarchy of a 1024^2 near-critical lattice is built by the GPU
+    setup, exported to the host and solved by the C port: a MEASURED solve at 1024^2, scaled only x16 sites to 4096^2.
+The JSON says all of this in `sample`.  The reference's own binary IS timed on the configuration it can run (BASELINE
+configs[1], key `config2_vs_reference_binary`).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -112,14 +117,12 @@ def post_sweeps(nlevels):
 
 
 # ---------------------------------------------------------------------------------------------------------
-CPU_SAMPLE_L = int(os.environ.get("MG2D_CPU_SAMPLE_L", "256"))   # lattice of the bounded CPU sample (workload's hierarchy shape)
-CPU_SAMPLE_ITERS = 6      # outer iterations timed per sample (~7 s of numpy work at 256^2)
+CPU_SAMPLE_L = int(os.environ.get("MG2D_CPU_SAMPLE_L", "512"))   # lattice of the bounded CPU sample of the reference arm
 
 
 def oracle_setup(L_cpu: int):
     """Hierarchy of the numpy oracle on a bounded sample of the workload: same shape (block 4, 16 coarse dof,
     rbgs post-only 4/2/8.., GCR(8)), lattice L_cpu.  Not timed."""
-    import copy
     import numpy as np
     from oracle import mg_oracle as O
     nlevels = max(1, int(round(math.log(L_cpu / 16, 4))))
@@ -131,29 +134,53 @@ def oracle_setup(L_cpu: int):
     O.compute_near_null(LVL, NTL, po, 1)
     b = np.zeros((L_cpu * L_cpu, 2), dtype=complex)
     b[L_cpu // 2 + (L_cpu // 2) * L_cpu, 0] = 1.0
-    return {"O": O, "po": po, "LVL": LVL, "NTL": NTL, "b": b, "L": L_cpu, "copy": copy}
+    from oracle import c_port
+    return {"levels": c_port.levels_from_oracle(LVL, po), "size": po.size, "n_dof": po.n_dof, "pre": po.pre, "post": po.post,
+            "b": b, "L": L_cpu, "how": f"hierarchy of a {L_cpu}^2 lattice (m = -0.05) set up by the numpy oracle"}
 
 
-def oracle_solve(st, budget_s: float = 8.0):
-    """CPU sample: full solves (to 1e-10) of the bounded-sample problem with the C + OpenMP port of the solve loop
-    (oracle/c_port, all host threads), repeated until `budget_s` seconds of CPU work are accumulated; falls back to the
-    numpy oracle if the C port cannot be built.  Returns (seconds per site*iteration, iterations per solve, seconds, kind)."""
-    try:
-        from oracle import c_port
-        c_port.build()
-        tot_s, tot_it, reps = 0.0, 0, 0
-        while tot_s < budget_s and reps < 200:
-            _, info = c_port.gcr_solve(st["LVL"], st["po"], st["b"], tol=TOL, max_iters=200, restart=8)
-            tot_s += info["seconds"]
-            tot_it += info["iters"]
-            reps += 1
-        return tot_s / (tot_it * st["L"] ** 2), tot_it // reps, tot_s, f"C+OpenMP port (oracle/c_port), {reps} full solves"
-    except Exception as e:      # no compiler on the box: numpy port
-        LVL = st["copy"].deepcopy(st["LVL"])
-        t0 = time.perf_counter()
-        _, info = st["O"].gcr_MG(LVL, st["NTL"], st["po"], st["b"], tol=TOL, max_iters=CPU_SAMPLE_ITERS, restart=8)
-        dt = time.perf_counter() - t0
-        return dt / (info["iters"] * st["L"] ** 2), info["iters"], dt, f"numpy port ({type(e).__name__}: C port unavailable), {info['iters']} iterations"
+def gpu_export_setup(mg2d, critical, L_cpu: int, delta: float):
+    """cpu_baseline of the GPU arm: a near-critical L_cpu^2 hierarchy of the workload's shape built by the GPU setup and
+    exported to host arrays in the reference's layouts (D[s][k][i][j], dense P) for the C port.  Not timed."""
+    import numpy as np
+    import torch
+    U = mg2d.gauge.quenched_links_device(L_cpu, 6.0, sweeps=60, seed=1234)
+    mcrit, _ = critical.estimate_critical_mass(U, lambda m: workload_params(mg2d, L_cpu, m), iters=4, refine=3)
+    p = workload_params(mg2d, L_cpu, mcrit + delta, matrix_free=False)
+    mg = mg2d.setup(U, p, init="device")
+    levels = []
+    for l, lv in enumerate(mg.LVL):
+        levels.append({"D": mg2d.D_to_reference_layout(lv.D).cpu().numpy(),
+                       "P": lv.phi_null.cpu().numpy() if l < p.nlevels else None})
+    b = np.zeros((L_cpu * L_cpu, 2), dtype=complex)
+    b[L_cpu // 2 + (L_cpu // 2) * L_cpu, 0] = 1.0
+    # the GPU's own solve of this problem, for the iteration count the CPU solve is expected to reproduce
+    rhs = torch.as_tensor(b).cuda()
+    _, info = mg2d.solve(mg, rhs=rhs, tol=TOL, outer="gcr", restart=8)
+    out = {"levels": levels, "size": p.size, "n_dof": p.n_dof, "pre": p.pre, "post": p.post, "b": b, "L": L_cpu,
+           "gpu_iters": info["iters"],
+           "how": f"hierarchy of a near-critical {L_cpu}^2 lattice (m_crit {mcrit:+.5f} + {delta:g}) built by the GPU setup and exported to the host"}
+    mg.close()
+    return out
+
+
+def cpu_solves(st, budget_s: float):
+    """Full solves (to 1e-10) of the sample problem with the C + OpenMP port of the solve loop on every host processor,
+    repeated until `budget_s` seconds of CPU work are accumulated (at least one).  Returns dict(seconds per solve, iters,
+    threads, reps, total seconds)."""
+    from oracle import c_port
+    c_port.build()
+    tot_s, its, reps, threads = 0.0, [], 0, 0
+    while reps == 0 or (tot_s < budget_s and reps < 200):
+        _, info = c_port.gcr_solve_arrays(st["levels"], st["size"], st["n_dof"], st["pre"], st["post"], 4, st["b"], tol=TOL,
+                                          max_iters=200, restart=8, threads=None)
+        if not info["converged"]:
+            raise RuntimeError("CPU port did not converge on the sample problem")
+        tot_s += info["seconds"]
+        its.append(info["iters"])
+        threads = info["threads"]
+        reps += 1
+    return {"s_per_solve": tot_s / reps, "iters": its[-1], "threads": threads, "reps": reps, "total_s": tot_s}
 
 
 def run_reference_arm(args):
@@ -162,24 +189,29 @@ def run_reference_arm(args):
     if rank != 0:
         return
     L = args.L
-    cores = os.cpu_count() or 1
-    iters_gpu = args.ref_iters
+    t0 = time.perf_counter()
     st = oracle_setup(CPU_SAMPLE_L)
-    for _ in range(args.warmup):
-        oracle_solve(st, 1.0)
-    vals = []
+    t_setup = time.perf_counter() - t0
+    scale = (L / st["L"]) ** 2
+    for _ in range(min(args.warmup, 2)):
+        cpu_solves(st, 0.0)
+    vals, walls, res = [], [], None
     for _ in range(args.steps):
-        per_site_iter, it_done, dt, how = oracle_solve(st, 6.0)
-        vals.append(per_site_iter * L * L * iters_gpu * 1e3)
+        t0 = time.perf_counter()
+        res = cpu_solves(st, 0.0)                 # one full solve per step
+        walls.append((time.perf_counter() - t0) * 1e3)
+        vals.append(res["s_per_solve"] * 1e3 * scale)
     v = sum(vals) / len(vals)
-    sample = (f"{how} on a {CPU_SAMPLE_L}^2 lattice with the workload's hierarchy shape (block 4, 16 coarse dof, red-black post-smoothing "
-              f"4/2/8.., FGCR(8), {it_done} iterations per solve), ~6 s of CPU work per step on {cores} threads; scaled per site and "
-              f"per iteration to {L}^2 x {iters_gpu} iterations (extrapolated)")
+    sample = (f"C+OpenMP port (oracle/c_port) on {res['threads']} OpenMP threads (set explicitly): one full solve to {TOL:g} per step "
+              f"({res['iters']} iterations, the count the CPU solve itself needs) on the {st['how']} with the workload's hierarchy shape "
+              f"(block 4, 16 coarse dof, red-black post-smoothing 4/2/8.., FGCR(8)); oracle setup {t_setup:.0f} s not timed; "
+              f"value = measured solve time x {scale:g} sites ({st['L']}^2 -> {L}^2, extrapolated); ms_per_step = measured wall time of a step")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": sum(walls) / len(walls), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
-            "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "tol": TOL, "iters": iters_gpu},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "tol": TOL, "iters": res["iters"],
+                       "sample_L": st["L"], "extrapolated": True, "site_scale": scale},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -256,8 +288,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=4096)
     ap.add_argument("--delta", type=float, default=1e-3, help="mass offset above the estimated critical mass")
-    ap.add_argument("--ref-iters", type=int, default=20,
-                    help="outer iterations of the workload solve (20 measured by the GPU arm at 4096^2) used to scale the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra solve (+ one D-apply) with cudaProfilerStart/Stop for `ncu --profile-from-start off`; "
@@ -299,12 +329,29 @@ def main():
         mcrit = dist_mod.bcast_float(comm, critical.estimate_critical_mass(
             U, lambda m: workload_params(mg2d, L, m), iters=4, refine=3)[0] if rank == 0 else 0.0)
     mass = mcrit + args.delta
-    import gc
     gc.collect()
     torch.cuda.empty_cache()
     torch.cuda.synchronize()
     t_crit = time.time() - t0
     p = workload_params(mg2d, L, mass)
+    # N > 1: rank 0 first solves the SAME problem on one GPU; the strip solve must need the same number of iterations
+    # (the hierarchy is partition-invariant: counter-based near-null seeds keyed on the global site index)
+    ref_n1 = None
+    if comm is not None:
+        t = torch.zeros(3, dtype=torch.float64, device=dev)
+        if rank == 0:
+            ref = mg2d.setup(U, p, init="device")
+            rr = torch.zeros((L * L, 2), dtype=torch.complex128, device=dev)
+            rr[L // 2 + (L // 2) * L, 0] = 1.0
+            xr, ir = mg2d.solve(ref, rhs=rr, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1)
+            x_ref_strip = xr[:(L // world) * L].clone()          # rank 0's strip of the single-GPU solution
+            t[0], t[1] = ir["iters"], ir["true_resnorm"]
+            ref.close()
+            del ref, rr, xr
+            gc.collect()
+            torch.cuda.empty_cache()
+        torch.distributed.broadcast(t, 0)
+        ref_n1 = {"iters": int(t[0].item()), "true_resnorm": float(t[1].item())}
     t0 = time.time()
     mg = mg2d.setup(U, p, init="device") if comm is None else dist_mod.setup(U, p, comm)
     torch.cuda.synchronize()
@@ -332,6 +379,11 @@ def main():
         x, info = one_solve()
     barrier()
     log(f"timed solves (iters {info['iters']}, true residual {info.get('true_resnorm')})")
+    if ref_n1 is not None:
+        ref_n1["iters_match_n1"] = bool(info["iters"] == ref_n1["iters"])
+        if rank == 0:
+            ref_n1["x_rel_diff_vs_n1"] = float((x[:x_ref_strip.shape[0]] - x_ref_strip).abs().max() / x_ref_strip.abs().max())
+            del x_ref_strip
     n0 = mg.launches
     sampler = ClockSampler(local)
     sampler.start()
@@ -477,13 +529,20 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): bounded oracle sample, scaled ----------------------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        Lc = CPU_SAMPLE_L
-        per_site_iter, it_done, t_cpu, how = oracle_solve(oracle_setup(Lc), 10.0)
-        cpu = {"value": per_site_iter * L * L * info["iters"] * 1e3, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": (f"{how}, same algorithm on a {Lc}^2 lattice (block 4, 16 coarse dof, red-black post-smoothing 4/2/8.., FGCR(8), "
-                          f"{it_done} iterations per solve), {t_cpu:.1f} s of CPU work; scaled per site x iteration to {L}^2 x "
-                          f"{info['iters']} iterations (extrapolated)")}
-
+        try:
+            Lc = min(1024, L)
+            stc = gpu_export_setup(mg2d, critical, Lc, args.delta)
+            res = cpu_solves(stc, 10.0)
+            scale = (L / Lc) ** 2
+            cpu = {"value": res["s_per_solve"] * 1e3 * scale, "unit": UNIT, "cores": res["threads"], "kind": "port",
+                   "measured_ms": res["s_per_solve"] * 1e3, "measured_L": Lc, "site_scale": scale,
+                   "sample": (f"C+OpenMP port (oracle/c_port) on {res['threads']} OpenMP threads (set explicitly): {res['reps']} full solves to "
+                              f"{TOL:g} ({res['iters']} iterations each; the GPU needs {stc['gpu_iters']} on the same problem), {res['total_s']:.1f} s of CPU "
+                              f"work, on the {stc['how']}: {res['s_per_solve']*1e3:.0f} ms per solve MEASURED at {Lc}^2; value = that x {scale:g} sites "
+                              f"({Lc}^2 -> {L}^2)")}
+            del stc
+        except Exception as e:      # the CPU leg must never break the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {type(e).__name__}: {e}"[:300]}
     config2 = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -498,6 +557,8 @@ def main():
         "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "hbm_gb_in_use": round(torch.cuda.max_memory_allocated() / 1e9, 1), "plaquette": plaq, "mass": mass,
                    "m_crit_est": mcrit, "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
                    "smoother": "rbgs, pre 0, post " + str(p.post), "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
+                   "executed_iters": info.get("executed_iters"), "n1_reference": ref_n1,
+                   "iters_match_n1": (None if ref_n1 is None else ref_n1["iters_match_n1"]),
                    "final_true_residual": info.get("true_resnorm"), "converged": info["converged"],
                    "setup_s": t_setup, "mcrit_s": t_crit, "cache": "working set >> L2 (126 MB); kernel timings flush L2 with a 256 MiB write",
                    "parallelism": f"strip{world}"},

@@ -34,6 +34,7 @@ extern "C" {
 #endif
 
 typedef struct mg2d_ctx mg2d_ctx;
+struct mg2d_halo_link;
 
 enum { MG2D_C128 = 0, MG2D_C64 = 1 };
 enum { MG2D_OK = 0, MG2D_EINVAL = -1, MG2D_ECUDA = -2, MG2D_EUNSUPPORTED = -3 };
@@ -99,16 +100,17 @@ int mg2d_wilson_relax_rb(mg2d_ctx*, void* phi, const void* phi_lo, const void* p
  * -1 / Ly of r (r == NULL: r = 0).  On one GPU these are the periodic wrap rows of the arrays themselves. */
 int mg2d_wilson_relax_rb2(mg2d_ctx*, void* out, const void* in, const void* in_lo2, const void* in_hi2,
                           const void* U, const void* U_lo2, const void* U_hi, const void* r, const void* r_lo,
-                          const void* r_hi, double mass, int Lx, int Ly, int yoff, int dtype, void* stream);
+                          const void* r_hi, double mass, int Lx, int Ly, int yoff, int dtype,
+                          const struct mg2d_halo_link* link, void* stream);
 
 /* The same half sweep on pre-multiplied hopping blocks M[s][k-1][j][i] = -D0inv(s) D_k(s), k = 1..4 (built once by
  * mg2d_premultiply): phi(s) <- sum_k M_k(s) phi(s+d_k) + c(s), c = D0inv r.  4 blocks per updated site instead of 5.
  * cmode 0: r = 0; 1: first sweep of a relax call (c computed from D0inv, r and stored in cbuf[nvec][S][n]);
- * 2: c read from cbuf. */
+ * 2: c read from cbuf.  link (may be NULL): fused neighbour push / wait on strips, see mg2d_halo_link. */
 int mg2d_premultiply(mg2d_ctx*, void* M, const void* D, const void* D0inv, int n, long long nsites, int dtype, void* stream);
 int mg2d_relax_rb_pm(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* M, const void* D0inv,
                      const void* r, void* cbuf, int cmode, int n, int Lx, int Ly, int colour, int yoff, int dtype,
-                     int nvec, long long vstride, long long hstride, void* stream);
+                     int nvec, long long vstride, long long hstride, const struct mg2d_halo_link* link, void* stream);
 
 /* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
  * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64
@@ -133,13 +135,14 @@ int mg2d_axpy_ratio2(mg2d_ctx*, void* y, const void* x, void* y2, const void* x2
  * directions W_j / Z_j (`stride` elements apart), one pass each:
  *   mg2d_gcr_dots : out[2j..2j+1] = <W_j, w>
  *   mg2d_gcr_ortho: w -= sum_j (dots_j / wn2_j) W_j ; z -= sum_j (...) Z_j ; out = { |w|^2, Re<w,r>, Im<w,r> } of the new w
- *   mg2d_gcr_step : a = <w,r>/|w|^2 (wr = the three doubles above); x += a z ; r -= a w ; out[0] = |r|^2 */
+ *   mg2d_gcr_step : a = <w,r>/|w|^2 (wr = the three doubles above); x += a z ; r -= a w ; out[0] = |r|^2 ;
+ *                   *wn2_slot = |w|^2 (kept for the projections of later iterations) */
 int mg2d_gcr_dots(mg2d_ctx*, const void* W, long long stride, int nj, const void* w, long long nelem, int dtype,
                   double* out, void* stream);
 int mg2d_gcr_ortho(mg2d_ctx*, void* w, void* z, const void* r, const void* W, const void* Z, long long stride, int nj,
                    const double* dots, const double* wn2, long long nelem, int dtype, double* out, void* stream);
-int mg2d_gcr_step(mg2d_ctx*, void* x, void* r, const void* z, const void* w, const double* wr, long long nelem,
-                  int dtype, double* out, void* stream);
+int mg2d_gcr_step(mg2d_ctx*, void* x, void* r, const void* z, const void* w, const double* wr, double* wn2_slot,
+                  long long nelem, int dtype, double* out, void* stream);   /* wn2_slot (may be NULL) receives |w|^2 */
 int mg2d_zero(mg2d_ctx*, void* x, long long nelem, int dtype, void* stream);
 int mg2d_copy(mg2d_ctx*, void* dst, const void* src, long long nelem, int dtype, void* stream);
 /* dst = src converted between MG2D_C128 and MG2D_C64 */
@@ -204,6 +207,28 @@ int mg2d_scale_phi(mg2d_ctx*, void* phi, void* e, long long estride, const doubl
                    long long nelem, int dtype, void* stream);
 
 /* ---- multi-GPU strips: peer-to-peer halo exchange over NVLink (no reference counterpart) ------- */
+/* Neighbour push fused into a smoother kernel.  The kernel processes its boundary rows LAST; before it reads the halo
+ * rows it waits (wait != 0) until both neighbours' flags in `slot_mine` have reached the local epoch, it stores the
+ * boundary rows it produces straight into the neighbours' halo buffers (peer-mapped pointers, NULL = no push) and its
+ * last CTA releases the neighbours' flags with epoch + 1: no separate exchange launch, the interior overlaps the
+ * transfer.  Slots are the 64-byte records mg2d_halo_exchange uses. */
+typedef struct mg2d_halo_link {
+    void* slot_mine; void* slot_prev; void* slot_next;
+    void* push_next_lo; void* push_prev_hi;
+    int wait;
+} mg2d_halo_link;
+/* Reductions summed over all ranks INSIDE the producing kernel: every rank owns a mailbox (mg2d_comm_mailbox_bytes()
+ * bytes of zeroed, peer-mapped memory); mg2d_comm_create builds the descriptor from the `world` mailbox pointers as seen
+ * from this rank and attaches it; while mg2d_comm_reduce(ctx, 1) is in force the `dots` / norm outputs of
+ * mg2d_wilson_apply, mg2d_stencil_apply (nvec = 1), mg2d_norm2 and mg2d_gcr_* are global sums, bit-identical on every
+ * rank (contributions added in rank order).  mg2d_allreduce sums n <= 64 doubles in place (batched reductions). */
+int mg2d_comm_mailbox_bytes(void);
+int mg2d_comm_create(mg2d_ctx*, int world, int rank, void* const* mailbox_ptrs, void** desc_out);
+int mg2d_comm_attach(mg2d_ctx*, void* desc);                   /* share one descriptor between handles of one rank */
+int mg2d_comm_reduce(mg2d_ctx*, int on);
+int mg2d_comm_error(mg2d_ctx*, void* desc, long long* out);    /* synchronous: non-zero after a peer time-out */
+int mg2d_allreduce(mg2d_ctx*, double* buf, int n, void* stream);
+int mg2d_halo_errors(mg2d_ctx*, const void* slots, int nslots, long long* out);   /* synchronous */
 /* A slab of device memory other ranks can map (CUDA IPC): cudaMalloc + zero + 64-byte handle. */
 int mg2d_ipc_alloc(mg2d_ctx*, long long bytes, void** ptr, void* handle64);
 int mg2d_ipc_open(mg2d_ctx*, const void* handle64, void** ptr);

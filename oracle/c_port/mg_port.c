@@ -12,6 +12,7 @@
  */
 #include <complex.h>
 #include <math.h>
+#include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -192,3 +193,12 @@ int mgport_gcr_solve(int nlevels, level_t* lv, const int* pre, const int* post, 
 }
 
 int mgport_level_size(void) { return (int)sizeof(level_t); }
+
+
+/* Thread count of the solve loops: n > 0 sets it explicitly (launchers such as torch.distributed.run export
+ * OMP_NUM_THREADS=1, which would silently serialise the CPU arm), n <= 0 uses every processor.  Returns the count in force. */
+int mgport_set_threads(int n) {
+    omp_set_dynamic(0);
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+    return omp_get_max_threads();
+}

@@ -101,6 +101,63 @@ def make_large(reuse=None):
         print(f"{name}: iters {iters} final printed residual {resmag[-1]}")
 
 
+# Cycle pinned without the near-null generation in the loop: the reference is run twice in the same directory, first with
+# gen_null = 1 (writes Near-null_*.txt, S6/modules_main.h:62-79), then with gen_null = 0 (reads it back, :39-60).  The
+# fixture keeps the file's vectors (25 digits), so oracle / GPU start from the reference's OWN near-null vectors and the
+# residual history can be demanded to 1e-9: it is recomputed at full precision from results_res_lvl-0.txt (the residual
+# vector the reference writes at the start of every iteration, S6/level.h:266-285) instead of the 6-digit printout.
+GN0_CASES = [
+    ("gn0_s6_laplace16_2lvl", "laplace", 16, 3, 2, 0.05, 2, 0, 1, 30),
+    ("gn0_s6_laplace16_ntl4", "laplace", 16, 3, 2, 0.05, 2, 1, 4, 30),
+    ("gn0_s6_wilson16_ntl4", "wilson", 16, 3, 2, 0.05, 2, 1, 4, 30),
+]
+
+
+def make_gn0():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    for name, stencil, L, ni, blk, m, nl, tf, nco, sweeps in GN0_CASES:
+        exe = os.path.join(ROOT, "oracle", "_ref", "s6_mgrid_ntl" + ("_laplace" if stencil == "laplace" else ""))
+        theta = O.gauge_quenched_phases(L, 32.0, sweeps=sweeps, seed=1234)
+        n0, nc = (2, 4) if stencil == "wilson" else (1, 2)
+        with tempfile.TemporaryDirectory() as d:
+            run = os.path.join(d, "run")
+            os.makedirs(run)
+            os.makedirs(os.path.join(d, "gauge_config_files"))
+            O.write_phase_file(os.path.join(d, "gauge_config_files", f"phase_{L}_b32.0.dat"), theta, L)
+            argv = [str(L), str(ni), str(blk), "1", repr(m), str(nl), str(tf), str(nco)]
+            subprocess.run([exe] + argv, cwd=run, capture_output=True, text=True, timeout=600)
+            argv[3] = "0"
+            out = subprocess.run([exe] + argv, cwd=run, capture_output=True, text=True, timeout=600).stdout
+            iters = int(re.search(r"Ans (\d+)", out).group(1))
+            vals = []
+            with open(os.path.join(run, f"Near-null_L{L}_blk{blk}_ndof{nc}.txt")) as f:
+                for line in f:
+                    a, b = line.strip().split("+i")
+                    vals.append(float(a) + 1j * float(b))
+            vals = np.array(vals)
+            nulls, off, size, ndof = {}, 0, [L // blk ** k for k in range(nl + 1)], [n0] + [nc] * nl
+            for lvl in range(nl):
+                cnt = size[lvl] ** 2 * ndof[lvl + 1] * ndof[lvl]
+                nulls[f"null{lvl}"] = vals[off:off + cnt].reshape(size[lvl] ** 2, ndof[lvl + 1], ndof[lvl])
+                off += cnt
+            assert off == len(vals)
+            # the second run appended to the result files of the first: keep the rows of the LAST run (iteration labels restart at 1)
+            rows = parse_cplx_rows(os.path.join(run, "results_res_lvl-0.txt"), L, n0)
+            start = max(i for i, (lab, _) in enumerate(rows) if lab == 1)
+            rows = rows[start:]
+            res_norm = np.array([np.sqrt(np.sum(np.abs(v) ** 2)) for _, v in rows])
+            phis = parse_cplx_rows(os.path.join(run, "results_phi.txt"), L, n0)
+            w = np.zeros((0, 4), dtype=complex)
+            if tf:
+                wr = open(os.path.join(run, "results_NTL_weights.txt")).read().strip().split("\n")
+                wr = [r for r in wr if r]
+                w = np.array([[complex(float(x.split("+i")[0]), float(x.split("+i")[1])) for x in r.rstrip(",").split(",")[1:]] for r in wr])
+                w = w[-iters:]
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), argv=np.array(argv), stencil=stencil, theta=theta,
+                            iters=iters, res_norm=res_norm, phi_final=phis[-1][1], ntl_weights=w, **nulls)
+        print(f"{name}: iters {iters} rows {len(res_norm)} final |r| {res_norm[-1]:.3e}")
+
+
 def parse_cplx_rows(path, L, n):
     rows = open(path).read().strip().split("\n")
     out = []
@@ -146,7 +203,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "--large":
+    if len(sys.argv) > 1 and sys.argv[1] == "--gn0":
+        make_gn0()
+    elif len(sys.argv) > 1 and sys.argv[1] == "--large":
         make_large(sys.argv[2] if len(sys.argv) > 2 else None)
     else:
         main()

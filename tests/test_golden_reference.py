@@ -72,3 +72,58 @@ def test_gpu_matches_reference_run(path):
     mg, info = mg2d.run_reference_flow(p, U)
     check(z, cfg, info["iters"], info["resnorms"], mg.LVL[0].phi.cpu().numpy(),
           mg.LVL[0].phi_null.cpu().numpy() if cfg["nlevels"] > 0 else None, info["ntl_weights"])
+
+
+# ---- the cycle alone, pinned tightly: the reference run with gen_null = 0 on its OWN near-null file ----------------------
+GN0 = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "gn0_s6_*.npz")))
+
+
+def check_gn0(z, cfg, iters, resnorms, bnorm, phi, weights):
+    """Identical iteration count; residual history to 1e-9 (full-precision residual vectors of results_res_lvl-0.txt,
+    S6/level.h:266-285; floor = rounding of the iterates); final phi to 1e-9; NTL weights to their 5 printed digits."""
+    assert iters == int(z["iters"])
+    ref = z["res_norm"]                       # row 0: before the first cycle; row k: after cycle k; last row repeats the final state
+    assert len(ref) == iters + 1
+    for k in range(iters):
+        a, b = resnorms[k] * bnorm, ref[k + 1]
+        assert abs(a - b) <= 1e-9 * b + 2e-13 * ref[0], (k, a, b)
+    assert np.max(np.abs(phi - z["phi_final"])) < 1e-9 * np.max(np.abs(z["phi_final"]))
+    if cfg["t_flag"]:
+        w, nco = z["ntl_weights"], cfg["n_copies"]
+        assert len(w) == iters
+        for k in range(iters):
+            if k > 0 and resnorms[k - 1] < 1e-11:
+                break      # the 4x4 min-res system is rounding noise once the residual is at 1e-12 (weights differ at 1e-3 there)
+            assert np.max(np.abs(np.asarray(weights[k])[:nco] - w[k][:nco])) < 1e-4 * np.max(np.abs(w[k][:nco])), k
+
+
+def test_gn0_fixtures_present():
+    assert len(GN0) >= 3
+
+
+@pytest.mark.parametrize("path", GN0, ids=[os.path.basename(p)[:-4] for p in GN0])
+def test_oracle_cycle_matches_reference_on_its_own_null_vectors(path):
+    z, cfg = load(path)
+    p = O.Params(**cfg)
+    LVL, NTL = O.build_reference_problem(p, O.gauge_from_phases(z["theta"]))
+    for lvl in range(p.nlevels):
+        LVL[lvl].phi_null = z[f"null{lvl}"].copy()                      # f_read_near_null, S6/modules_main.h:39-60
+    O.compute_near_null(LVL, NTL, p, p.quad, gen_null=0)
+    bnorm = float(np.sqrt(np.sum(np.abs(LVL[0].r) ** 2)))
+    info = O.perform_MG(LVL, NTL, p)
+    check_gn0(z, cfg, info["iters"], info["resnorms"], bnorm, LVL[0].phi, info["ntl_weights"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GN0, ids=[os.path.basename(p)[:-4] for p in GN0])
+def test_gpu_cycle_matches_reference_on_its_own_null_vectors(path):
+    import torch
+    import mg2d
+    z, cfg = load(path)
+    p = mg2d.make_params(cfg["L"], cfg["m"], stencil=cfg["stencil"], nlevels=cfg["nlevels"], block=cfg["block"],
+                         n_smooth=cfg["num_iters"], smoother="gs", ntl=bool(cfg["t_flag"]), n_copies=cfg["n_copies"])
+    U = torch.as_tensor(O.gauge_from_phases(z["theta"])).cuda()
+    mg = mg2d.setup(U, p, null_vectors=[torch.as_tensor(z[f"null{lvl}"]) for lvl in range(p.nlevels)], init="reference")
+    bnorm = float(torch.linalg.vector_norm(mg.LVL[0].r).item())
+    x, info = mg2d.solve(mg)
+    check_gn0(z, cfg, info["iters"], info["resnorms"], bnorm, x.cpu().numpy(), info["ntl_weights"])
