@@ -4,9 +4,10 @@
 
 Same 8 positional arguments as `./a.out` (S6/params.h:42-50), same inputs (`../gauge_config_files/phase_{L}_b{beta}.dat`,
 S6/gauge.h:44; `Near-null_L*_blk*_ndof*.txt` when gen_null = 0, S6/modules_main.h:39-60) and the same outputs in the
-working directory: `results_gen_scaling.txt` (appended row, S6/modules_main.h:472), `results_phi.txt` (final phi row,
-S6/level.h:287-300), `Near-null_*.txt` (when gen_null = 1) and the "Ans" line on stdout.  The per-iteration text dumps
-of the reference (write_interval = 1) are not reproduced: only the final state is written.
+working directory: `results_gen_scaling.txt` (appended row, S6/modules_main.h:472), `results_phi.txt`,
+`results_res_lvl-%d.txt` and `results_NTL_weights.txt` (one row per iteration as the reference writes them,
+S6/modules_main.h:446-458, S6/level.h:266-300, S6/modules_indiv.h:137-143; --write-interval k thins them out),
+`Near-null_*.txt` (when gen_null = 1) and the "Ans" line on stdout.
 """
 from __future__ import annotations
 
@@ -23,6 +24,9 @@ def main(argv=None):
     ap.add_argument("args", nargs=8, help="L num_iters block gen_null m nlevels t_flag n_copies")
     ap.add_argument("--stencil", default="wilson", choices=["wilson", "laplace"])
     ap.add_argument("--beta", type=float, default=32.0)
+    ap.add_argument("--write-interval", type=int, default=1,
+                    help="write results_phi / results_res_lvl-* rows every k-th iteration (reference: 1, S6/params.h:65); "
+                         "0: only the final phi row")
     ns = ap.parse_args(argv)
     gen_null = int(ns.args[3])
     p = mg2d.from_argv(ns.args, stencil=ns.stencil)
@@ -43,7 +47,9 @@ def main(argv=None):
     mg = mg2d.setup(U, p, null_vectors=nulls, init="reference")
     if gen_null == 1 and p.nlevels > 0:
         mg2d.refio.write_near_null(nn_file, [mg.LVL[l].phi_null for l in range(p.nlevels)])
-    x, info = mg2d.solve(mg)
+    writers = mg2d.refio.ResultWriters(".", p, stride=ns.write_interval) if ns.write_interval > 0 else None
+    info = mg2d.perform_MG(mg, on_iteration=None if writers is None else writers.on_iteration)
+    x = mg.LVL[0].phi
     if info["converged"]:
         print("\nLoop breaks at iteration %d with residue %e < %e" % (info["iters"], info["resnorms"][-1], p.tol))
         print("\nL %d\tm %f\tnlevels %d\tnum_per_level %d\tAns %d" % (p.L, p.mass, p.nlevels, p.n_smooth, info["iters"]))
@@ -51,8 +57,11 @@ def main(argv=None):
             f.write(mg2d.refio.gen_scaling_row(p.L, p.n_smooth, p.mass, p.block, p.n_dof_scale, p.nlevels, info["iters"]))
     elif info["diverged"]:
         print("\nDiverging. Residue %g at iteration %d" % (info["resnorms"][-1], info["iters"]))
-    with open("results_phi.txt", "w") as f:
-        mg2d.refio.write_results_phi_row(f, info["iters"], x, p.L)
+    if writers is not None:
+        writers.finish(mg, info)
+    else:
+        with open("results_phi.txt", "w") as f:
+            mg2d.refio.write_results_phi_row(f, info["iters"], x, p.L)
     return 0
 
 

@@ -91,6 +91,27 @@ class HaloLink(C.Structure):
 
 
 _lib = None
+TRACE_TAG = "-"                                          # multigrid level of the launches that follow (set by Level)
+TRACE = [] if os.environ.get("MG2D_TRACE") else None     # list of (entry point, start event, end event) when tracing
+
+
+def trace_begin():
+    global TRACE
+    TRACE = []
+
+
+def trace_report(reset: bool = True):
+    """{entry point: (calls, total ms)} of the traced launches (synchronises)."""
+    global TRACE
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in TRACE or []:
+        c, t = out.get(name, (0, 0.0))
+        out[name] = (c + 1, t + e0.elapsed_time(e1))
+    if reset:
+        TRACE = None
+    return out
 
 
 class MG2DError(RuntimeError):
@@ -131,9 +152,23 @@ class Context:
         self.device = device
 
     def call(self, name: str, *args):
+        if TRACE is not None:
+            return self._traced_call(name, *args)
         rc = getattr(self.lib, name)(self.h, *args)
         if rc != 0:
             raise MG2DError(f"{name} failed ({rc}): {self.lib.mg2d_last_error(self.h).decode()}")
+
+    def _traced_call(self, name: str, *args):
+        """MG2D_TRACE=1 (or trace_begin()): bracket every entry point with CUDA events on the current stream; trace_report()
+        sums the device time per entry point.  Eager launches only (events cannot be recorded into a graph capture)."""
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(self.lib, name)(self.h, *args)
+        e1.record()
+        if rc != 0:
+            raise MG2DError(f"{name} failed ({rc}): {self.lib.mg2d_last_error(self.h).decode()}")
+        TRACE.append((f"{name}@L{TRACE_TAG}", e0, e1))
 
     @property
     def launches(self) -> int:

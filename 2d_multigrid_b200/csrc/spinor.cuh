@@ -29,14 +29,16 @@ __device__ __forceinline__ Spinor<T> load_spinor_c(const cplx<T>* p, size_t s) {
     }
     return r;
 }
-// system-scope variant for halo rows a strip neighbour wrote over NVLink while this kernel was already running
+// halo rows a strip neighbour wrote over NVLink: read from L2 (ld.cg), the coherence point of peer stores -- never through
+// the non-coherent path.  Plain intrinsics, no inline asm, so the compiler keeps scheduling loads across it.
 template <typename T>
 __device__ __forceinline__ Spinor<T> load_spinor_sys(const cplx<T>* p, size_t s) {
     Spinor<T> r;
     if constexpr (sizeof(T) == 8) {
-        asm volatile("ld.volatile.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.c0.x), "=d"(r.c0.y), "=d"(r.c1.x), "=d"(r.c1.y) : "l"(p + 2 * s));
+        r.c0 = __ldcg(p + 2 * s); r.c1 = __ldcg(p + 2 * s + 1);
     } else {
-        asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.c0.x), "=f"(r.c0.y), "=f"(r.c1.x), "=f"(r.c1.y) : "l"(p + 2 * s));
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p) + s);
+        r.c0 = make_float2(v.x, v.y); r.c1 = make_float2(v.z, v.w);
     }
     return r;
 }

@@ -299,15 +299,9 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
             const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
             const long long st = (in_hi || in_lo) ? hstride : vstride;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                C val;
-                if (LINK && (in_hi || in_lo)) {       // peer-written memory: bypass L1
-                    const double2* q = reinterpret_cast<const double2*>(p + (size_t)v * st);
-                    if constexpr (sizeof(T) == 8) { val.x = ld_relaxed_sys_f64(&q->x); val.y = ld_relaxed_sys_f64(&q->y); }
-                    else { const double pk = ld_relaxed_sys_f64(reinterpret_cast<const double*>(p + (size_t)v * st)); val = *reinterpret_cast<const C*>(&pk); }
-                } else val = __ldcg(p + (size_t)v * st);
-                cfma(acc[v], d, val);
-            }
+            // (halo rows are peer-written: ld.cg reads them from L2, the coherence point of NVLink-incoming stores; no
+            // inline-asm loads here -- their compiler barrier would serialise the 32 independent loads of this loop)
+            for (int v = 0; v < NV; ++v) cfma(acc[v], d, __ldcg(p + (size_t)v * st));
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -331,7 +325,7 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
         }
     }
     if (LINK && push_lo) {
-        __threadfence_system();
+        if (waited || !link.wait) __threadfence_system();      // only CTAs that did boundary work have peer stores in flight
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);

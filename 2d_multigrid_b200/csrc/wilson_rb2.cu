@@ -207,7 +207,7 @@ wilson_rb2_kernel(Rb2Args<T> a) {
         }
     }
     if (linked && push_lo) {
-        __threadfence_system();
+        if (waited || !a.link.wait) __threadfence_system();    // only warps that did boundary work have peer stores in flight
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned long long t = atomicAdd(&a.link.mine->ticket, 1ull);

@@ -180,6 +180,7 @@ class Level:
 
     def _stencil(self, out, vin, b, mode, dots, nvec=1):
         mg = self.mg
+        _lib.TRACE_TAG = self.lvl
         if out.data_ptr() == vin.data_ptr():
             raise ValueError("stencil output must not alias its input")
         if self.matrix_free:
@@ -249,6 +250,7 @@ class Level:
         """f_relax (S6/level.h:100-128).  gs_flag 1 = lexicographic Gauss-Seidel, 0 = Jacobi (reference);
         smoother='mr' = minimal residual (north_star).  phi may be a batch [nvec, S, n]; r=None means r=0."""
         mg = self.mg
+        _lib.TRACE_TAG = self.lvl
         if smoother is None:
             smoother = mg.p.smoother if gs_flag is None else ("gs" if gs_flag == 1 else "jacobi")
         phi = self.phi if phi is None else phi
@@ -423,6 +425,7 @@ class Level:
     def restriction(self, vec_c, vec_f, quad: int):
         """f_restriction (S6/near_null.h:217-240): vec_c = P vec_f."""
         mg = self.mg
+        _lib.TRACE_TAG = self.lvl
         gather = self.distributed and not self._coarse_distributed()
         if self.distributed and quad != 1:
             raise MG2DError("shifted aggregates (quad != 1) need the whole lattice on one GPU")
@@ -443,6 +446,7 @@ class Level:
         accumulate=False writes vec_f = P^dagger vec_c (caller knows vec_f == 0; chirality-compacted path only)."""
         mg = self.mg
         blk = mg.p.block
+        _lib.TRACE_TAG = self.lvl
 
         def launch(vc_ptr, zv):
             if self.phi_null_c is not None:

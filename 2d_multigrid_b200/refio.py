@@ -54,3 +54,54 @@ def write_results_phi_row(f, it: int, phi, L: int) -> None:
 
 def gen_scaling_row(L, num_iters, m, block, n_dof_scale, nlevels, iters) -> str:
     return "%d\t%d\t%f\t%d\t%d\t%d\t%d\t%d\n" % (L, num_iters, m, block, block, n_dof_scale, nlevels, iters)
+
+
+def write_ntl_weights_row(f, it: int, a, total_copies: int = 4) -> None:
+    """One row of results_NTL_weights.txt (f_write_NTL_weights, S6/modules_indiv.h:137-143): total_copies = 4 entries."""
+    a = list(np.asarray(a).reshape(-1)) + [0j] * total_copies
+    f.write("%d," % it + "".join("%.4e+i%.4e," % (complex(z).real, complex(z).imag) for z in a[:total_copies]) + "\n")
+
+
+class ResultWriters:
+    """The reference's per-iteration result files (S6/params.h:89-97 open them, f_perform_MG writes them,
+    S6/modules_main.h:446-458, 469-475), so that its analysis notebooks (NB/7a, NB/8a) can read a GPU run unchanged:
+        results_phi.txt              row "iter+1, phi_0(x outer, y inner, dof)" at the START of iteration `iter` and once
+                                     more after convergence                                  (Level::f_write_op)
+        results_res_lvl-%d.txt       the residual r - D phi of every level, same rows       (Level::f_write_residue; with
+                                     t_flag the lowest level is NTL copy 0, modules_main.h:452-454)
+        results_NTL_weights.txt      row "iter, a_0..a_3" after every non-telescoping cycle  (f_write_NTL_weights)
+    The reference writes every iteration (write_interval = 1, S6/params.h:65), which costs a device->host copy of every
+    level per iteration; `stride` k writes every k-th iteration (and always the final state) and keeps the solve resident.
+    Use as  perform_MG(mg, on_iteration=w.on_iteration)  then  w.finish(mg, info)."""
+
+    def __init__(self, directory: str, p, stride: int = 1):
+        import os
+        self.p, self.stride = p, max(int(stride), 1)
+        self.f_phi = open(os.path.join(directory, "results_phi.txt"), "w")
+        self.f_w = open(os.path.join(directory, "results_NTL_weights.txt"), "w")
+        self.f_res = [open(os.path.join(directory, "results_res_lvl-%d.txt" % lvl), "w") for lvl in range(p.nlevels + 1)]
+        self.rows = 0
+
+    def _state_rows(self, label: int, mg, final: bool):
+        p = self.p
+        write_results_phi_row(self.f_phi, label, mg.LVL[0].phi, p.size[0])
+        for lvl in range(p.nlevels + 1):
+            lv = mg.NTL[lvl][0] if (p.ntl and lvl == p.nlevels and not final) else mg.LVL[lvl]
+            if lv.D is None and not lv.matrix_free or lv.phi is None or lv.r is None:
+                continue
+            rt = lv.work("rtemp")
+            lv.residue(rt)
+            write_results_phi_row(self.f_res[lvl], label, rt, p.size[lvl])
+        self.rows += 1
+
+    def on_iteration(self, it: int, mg):
+        if it % self.stride == 0:
+            self._state_rows(it + 1, mg, final=False)
+
+    def finish(self, mg, info):
+        for k, w in enumerate(info.get("ntl_weights", [])):
+            write_ntl_weights_row(self.f_w, k, w)
+        if info.get("converged"):
+            self._state_rows(info["iters"], mg, final=True)
+        for f in [self.f_phi, self.f_w] + self.f_res:
+            f.close()

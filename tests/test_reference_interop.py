@@ -107,6 +107,25 @@ def test_cli_drop_in(repo_root):
         assert os.path.exists(os.path.join(d, "run", mg2d.refio.near_null_filename(L, 2, 4)))
         row = open(os.path.join(d, "run", "results_gen_scaling.txt")).read().split()
         assert int(row[-1]) == ans and int(row[0]) == L
+
+        def rows(name):          # [(label, values)] of a per-iteration result file (S6/level.h:266-300)
+            out_ = []
+            for line in open(os.path.join(d, "run", name)).read().strip().split("\n"):
+                f = line.rstrip(",").split(",")
+                out_.append((int(f[0]), np.array([complex(float(x.split("+i")[0]), float(x.split("+i")[1])) for x in f[1:]])))
+            return out_
+        # per-iteration writers: one row per iteration (label iter+1, written at its start) plus the final state
+        names = ["results_phi.txt"] + ["results_res_lvl-%d.txt" % lvl for lvl in range(NL + 1)]
+        mine = {n: rows(n) for n in names}
+        for n in names:
+            assert len(mine[n]) == ans + 1 and [lab for lab, _ in mine[n]] == list(range(1, ans + 1)) + [ans], n
+        assert len(mine["results_res_lvl-0.txt"][0][1]) == L * L * 2 and len(mine["results_res_lvl-%d.txt" % NL][0][1]) == (L >> NL) ** 2 * 4
         if exe is not None:
             ref = subprocess.run([exe] + argv, cwd=os.path.join(d, "run"), capture_output=True, text=True, timeout=300).stdout
             assert int(re.search(r"Ans (\d+)", ref).group(1)) == ans
+            for n in names:      # the reference has just overwritten the files: same rows, same numbers
+                theirs = rows(n)
+                assert [lab for lab, _ in theirs] == [lab for lab, _ in mine[n]], n
+                for k in (0, 1, min(5, ans - 1), ans):
+                    a, b = mine[n][k][1], theirs[k][1]
+                    assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)) + 1e-13, (n, k)
