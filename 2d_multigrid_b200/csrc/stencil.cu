@@ -340,6 +340,62 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
     }
 }
 
+// ALL sweeps of one relax call on a small level in ONE cooperative launch: the half sweeps are separated by grid-wide
+// barriers instead of kernel boundaries.  On the levels that fit in L2 (<= a few thousand sites of 16x16 blocks) a half
+// sweep is a ~10 us launch that moves a few MB: pure latency, 16 of them per level and cycle, and on strips every rank pays
+// it in full because these levels are replicated.  Whole periodic lattice on this GPU, one vector.
+template <typename T, int N>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_pm_sweeps_kernel(cplx<T>* phi, const cplx<T>* __restrict__ M, const cplx<T>* __restrict__ Dinv,
+                            const cplx<T>* __restrict__ r, cplx<T>* cbuf, int L, int nsweeps) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    constexpr int JP = G / N;
+    constexpr int ITERS = (4 * N) / JP;
+    cg::grid_group grid = cg::this_grid();
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const int Lh = L / 2;
+    const long long S2 = (long long)Lh * L;
+    const long long nsteps = (S2 + GPB - 1) / GPB;
+    const C* lo = phi + (size_t)(L - 1) * L * N;
+    for (int it = 0; it < nsweeps; ++it) {
+        for (int colour = 0; colour < 2; ++colour) {
+            for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+                long long h = step * GPB + grp;
+                const bool active = h < S2;
+                if (!active) h = S2 - 1;
+                const int y = (int)(h / Lh);
+                const int x = 2 * (int)(h - (long long)y * Lh) + ((y + colour) & 1);
+                const size_t s = (size_t)y * L + x;
+                const C* Ms = M + s * 4 * N * N;
+                C acc = mk<T>(0, 0);
+#pragma unroll
+                for (int t = 0; t < ITERS; ++t) {
+                    const int k = 1 + (JP * t) / N;
+                    const int j = jp + (JP * t) % N;
+                    const C d = __ldg(Ms + g + G * t);
+                    cfma(acc, d, __ldcg(nbr_ptr<C>(phi, lo, phi, k, x, y, L, L, N) + j));
+                }
+#pragma unroll
+                for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
+                if (r) {
+                    if (it == 0) {
+                        const C c = apply_minus_inv<T, N, G>(Dinv + s * N * N, __ldg(r + s * N + i), g);     // = -D0^-1 r
+                        acc = csub(acc, c);
+                        if (active && jp == 0) cbuf[s * N + i] = mk<T>(-c.x, -c.y);
+                    } else {
+                        acc = cadd(acc, __ldcg(cbuf + s * N + i));
+                    }
+                }
+                if (active && jp == 0) phi[s * N + i] = acc;
+            }
+            grid.sync();
+        }
+    }
+}
+
 // M[s][k-1] = -D0inv[s] D[s][k], k = 1..4 (column-major blocks).  One CTA walks over sites; the site's D0^-1 and
 // the four hopping blocks are staged in shared memory.
 template <typename T, int N>
@@ -684,6 +740,42 @@ int dispatch_rb_pm(mg2d_ctx* ctx, int n, void* phi, const void* lo, const void* 
     }
 }
 
+template <typename T, int N>
+int launch_rb_pm_sweeps(mg2d_ctx* ctx, void* phi, const void* M, const void* Dinv, const void* r, void* cbuf, int L, int nsweeps,
+                        cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stencil_rb_pm_sweeps_kernel<T, N>, ST_THREADS, 0) != cudaSuccess || per_sm < 1)
+        return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_relax_rb_pm_sweeps: occupancy query failed");
+    const long long nsteps = ((long long)(L / 2) * L + GPB - 1) / GPB;
+    long long cap = (long long)(per_sm < 2 ? per_sm : 2) * ctx->num_sms;        // a small grid keeps the barrier cheap
+    int grid = (int)(nsteps < cap ? nsteps : cap);
+    C* phi_ = (C*)phi; const C* M_ = (const C*)M; const C* Dinv_ = (const C*)Dinv; const C* r_ = (const C*)r; C* cbuf_ = (C*)cbuf;
+    void* args[] = {&phi_, &M_, &Dinv_, &r_, &cbuf_, &L, &nsweeps};
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)stencil_rb_pm_sweeps_kernel<T, N>, args);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "mg2d_relax_rb_pm_sweeps: %s", cudaGetErrorString(e)); cudaGetLastError(); return MG2D_ECUDA; }
+    return mg2d_check_launch(ctx, "mg2d_relax_rb_pm_sweeps");
+}
+
+template <typename T>
+int dispatch_rb_pm_sweeps(mg2d_ctx* ctx, int n, void* phi, const void* M, const void* Dinv, const void* r, void* cbuf, int L,
+                          int nsweeps, cudaStream_t st) {
+    switch (n) {
+#define CASE(N) case N: return launch_rb_pm_sweeps<T, N>(ctx, phi, M, Dinv, r, cbuf, L, nsweeps, st)
+        CASE(1); CASE(2); CASE(4); CASE(8); CASE(16);
+#undef CASE
+        default: return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb_pm_sweeps: n_dof must be one of 1,2,4,8,16");
+    }
+}
+
 template <typename T>
 int dispatch_premul(mg2d_ctx* ctx, int n, void* M, const void* D, const void* Dinv, long long S, cudaStream_t st) {
     using C = cplx<T>;
@@ -829,4 +921,15 @@ extern "C" int mg2d_relax_rb_pm(mg2d_ctx* ctx, void* phi, const void* phi_lo, co
     if (dtype == MG2D_C128) return dispatch_rb_pm<double>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st);
     if (dtype == MG2D_C64)  return dispatch_rb_pm<float>(ctx, n, phi, phi_lo, phi_hi, M, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm: bad dtype");
+}
+
+extern "C" int mg2d_relax_rb_pm_sweeps(mg2d_ctx* ctx, void* phi, const void* M, const void* D0inv, const void* r, void* cbuf,
+                                       int n, int L, int nsweeps, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !M || L < 2 || (L & 1) || nsweeps < 1 || (r && (!D0inv || !cbuf)))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm_sweeps: bad argument (L must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MG2D_C128) return dispatch_rb_pm_sweeps<double>(ctx, n, phi, M, D0inv, r, cbuf, L, nsweeps, st);
+    if (dtype == MG2D_C64)  return dispatch_rb_pm_sweeps<float>(ctx, n, phi, M, D0inv, r, cbuf, L, nsweeps, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm_sweeps: bad dtype");
 }

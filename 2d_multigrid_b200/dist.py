@@ -56,7 +56,7 @@ def plan_strips(p: MGParams, world: int, min_rows: int = MIN_ROWS):
     plan, alive = [], True
     for lvl, L in enumerate(p.size):
         rows = L // world
-        ok = alive and L % world == 0 and rows >= min_rows and (lvl == p.nlevels or rows % p.block == 0)
+        ok = alive and L % world == 0 and rows >= min_rows and (lvl == p.nlevels or rows % p.blocks[lvl] == 0)
         alive = ok
         plan.append((ok, rows if ok else L))
     return plan

@@ -73,6 +73,7 @@ class Level:
         self.n = p.n_dof[lvl]
         self.S = self.L * self.Ly  # local sites
         self.nc = p.n_dof[lvl + 1] if lvl < p.nlevels else None
+        self.block = p.blocks[lvl] if lvl < p.nlevels else None      # aggregate size towards the next coarser level
         self.phi = None
         self.r = None
         self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
@@ -313,6 +314,13 @@ class Level:
                     cur, nxt = nxt, cur
                 if num_iter & 1:
                     mg.ctx.call("mg2d_copy", _ptr(nxt), _ptr(cur), vs, mg.dcode, _stream())
+        elif (smoother == "rbgs" and not self.matrix_free and not self.distributed and nvec == 1 and mg.premul and self.n <= 16
+              and mg.persistent_sites >= self.S and self.Ly == self.L and not (self.Dh is not None and mg.use_half)):
+            # small level: every sweep of this call in one cooperative launch (grid barriers instead of kernel boundaries)
+            self._ensure_M()
+            cbuf = None if r is None else self.work("pm_c")
+            mg.ctx.call("mg2d_relax_rb_pm_sweeps", _ptr(phi), _ptr(self.M), _ptr(self.D0inv), _ptr(r), _ptr(cbuf), self.n, self.L,
+                        num_iter, mg.dcode, _stream())
         elif smoother == "rbgs":
             hs = self.L * self.n if (self.distributed and nvec > 1) else vs
             for it in range(num_iter):
@@ -385,19 +393,19 @@ class Level:
     def norm_nn(self, quad: int):
         """f_norm_nn (S6/near_null.h:24-48)."""
         mg = self.mg
-        mg.ctx.call("mg2d_norm_nn", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad, mg.dcode, _stream())
+        mg.ctx.call("mg2d_norm_nn", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, self.block, quad, mg.dcode, _stream())
 
     def ortho(self, quad: int):
         """f_ortho (S6/near_null.h:97-173)."""
         mg = self.mg
-        mg.ctx.call("mg2d_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad, mg.dcode,
+        mg.ctx.call("mg2d_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, self.block, quad, mg.dcode,
                     _ptr(mg.status), _stream())
 
     def check_ortho(self, quad: int) -> float:
         """f_check_ortho (S6/near_null.h:175-214): worst |<null_d1, null_d2>| over aggregates."""
         mg = self.mg
         out = self.dots("ortho_check")
-        mg.ctx.call("mg2d_check_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, mg.p.block, quad,
+        mg.ctx.call("mg2d_check_ortho", _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly, self.block, quad,
                     mg.dcode, _ptr(out), _stream())
         self.allreduce(out[:1], "max")
         return float(out[0].item())
@@ -434,10 +442,10 @@ class Level:
             dst = self.work_coarse_strip()
         if self.phi_null_c is not None:
             mg.ctx.call("mg2d_restrict_chiral", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null_c), self.n, self.nc, self.L,
-                        self.Ly, mg.p.block, quad, mg.dcode, _stream())
+                        self.Ly, self.block, quad, mg.dcode, _stream())
         else:
             mg.ctx.call("mg2d_restrict", _ptr(dst), _ptr(vec_f), _ptr(self.phi_null), self.n, self.nc, self.L, self.Ly,
-                        mg.p.block, quad, mg.dcode, _stream())
+                        self.block, quad, mg.dcode, _stream())
         if gather:
             mg.comm.allgather(vec_c, dst)
 
@@ -445,7 +453,7 @@ class Level:
         """f_prolongation (S6/near_null.h:242-264): vec_f += P^dagger vec_c.  `self` is the FINE level.
         accumulate=False writes vec_f = P^dagger vec_c (caller knows vec_f == 0; chirality-compacted path only)."""
         mg = self.mg
-        blk = mg.p.block
+        blk = self.block
         _lib.TRACE_TAG = self.lvl
 
         def launch(vc_ptr, zv):
@@ -473,7 +481,7 @@ class Level:
         return bool(nxt is not None and nxt.distributed)
 
     def work_coarse_strip(self):
-        blk = self.mg.p.block
+        blk = self.block
         key = ("coarse_strip", None)
         if key not in self._work:
             self._work[key] = torch.zeros(((self.Ly // blk) * (self.L // blk), self.nc), dtype=self.mg.tdtype, device=self.mg.device)
@@ -498,6 +506,7 @@ class MG:
         self.info = {}
         self.use_half = False      # complex64 preconditioner copy: smooth with the half-precision operator blocks
         self.premul = True         # red-black sweeps on stored operators use the pre-multiplied blocks -D0^-1 D_k
+        self.persistent_sites = 8192   # levels with at most this many sites relax all sweeps of a call in one cooperative launch
         self.two_colour = True     # level-0 matrix-free red-black sweeps through the one-pass two-colour kernel
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
         self.min_rows = 0
@@ -643,14 +652,14 @@ def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
     p_lo, p_hi = lvl_f._halo(P, 1, nc * nf)          # projector rows below / above the strip (or the periodic wrap)
     if lvl_f.distributed and not lvl_c.distributed:
         # first replicated level: every rank builds its strip of D_c, then the strips are all-gathered
-        blk = mg.p.block
+        blk = lvl_f.block
         strip = torch.empty(((lvl_f.Ly // blk) * (lvl_f.L // blk), 5, nc, nc), dtype=mg.tdtype, device=mg.device)
         mg.ctx.call("mg2d_coarse_matrix", _ptr(strip), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.Ly,
                     blk, quad, mg.dcode, _stream())
         mg.comm.allgather(lvl_c.D, strip)
         return
     mg.ctx.call("mg2d_coarse_matrix", _ptr(lvl_c.D), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, nf, nc, lvl_f.L, lvl_f.Ly,
-                mg.p.block, quad, mg.dcode, _stream())
+                lvl_f.block, quad, mg.dcode, _stream())
 
 
 def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
@@ -726,6 +735,73 @@ def MG_simple(mg: MG, zero_start: bool = False):
                 prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], p.quad, accumulate=not fresh)
     else:
         LVL[0].relax(p.post[0])
+
+
+def _coarse_gcr(mg: MG, lvl: int):
+    """K-cycle coarse solve (ours): p.k_inner steps of flexible GCR on D_lvl phi = r_lvl from phi = 0, each
+    preconditioned by the K-cycle of this level (recursion).  A fixed number of steps: no residual test, no host sync.
+    Mirrors oracle _coarse_gcr."""
+    p = mg.p
+    lv = mg.LVL[lvl]
+    vs = lv.S * lv.n
+    kin = p.k_inner
+    call, dc, st = mg.ctx.call, mg.dcode, _stream
+    x, Z, W, sc = lv.work("k_x"), lv.work("k_Z", kin), lv.work("k_W", kin), lv.dots("kcyc")
+    call("mg2d_zero", _ptr(x), vs, dc, st())
+    keep = lv.phi
+    for j in range(kin):
+        z, w = Z[j], W[j]
+        call("mg2d_zero", _ptr(z), vs, dc, st())
+        lv.phi = z                       # the cycle writes its result in place; lv.r is the current residual
+        try:
+            MG_kcycle(mg, lvl)
+        finally:
+            lv.phi = keep
+        lv._stencil(w, z, None, _lib.MODE_APPLY, None)
+        if j > 0:
+            with lv.global_sums(sc[16:16 + 2 * j]):
+                call("mg2d_gcr_dots", _ptr(W), vs, j, _ptr(w), vs, dc, _ptr(sc[16:]), st())
+        with lv.global_sums(sc[0:4]):
+            call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(lv.r), _ptr(W), _ptr(Z), vs, j, _ptr(sc[16:]), _ptr(sc[40:]), vs, dc,
+                 _ptr(sc[0:]), st())
+        with lv.global_sums(sc[4:5]):
+            call("mg2d_gcr_step", _ptr(x), _ptr(lv.r), _ptr(z), _ptr(w), _ptr(sc[0:]), _ptr(sc[40 + j:]), vs, dc, _ptr(sc[4:]), st())
+    call("mg2d_copy", _ptr(lv.phi), _ptr(x), vs, dc, st())
+
+
+def MG_kcycle(mg: MG, lvl: int = 0, zero_start: bool = False):
+    """One K-cycle on level `lvl` (acts on LVL[lvl].phi / .r like f_MG_simple's body, S6/modules_main.h:255-280): pre-smooth,
+    restrict the residual, solve the coarse system with p.k_inner Krylov (FGCR) steps preconditioned by the K-cycle of the next
+    level instead of ONE recursive visit, prolong, post-smooth.  The coarsest level is only relaxed, as in the reference."""
+    p, LVL = mg.p, mg.LVL
+    lv = LVL[lvl]
+    if lvl == p.nlevels:
+        lv.relax(p.post[lvl])
+        return
+    lv.relax(p.pre[lvl])
+    if zero_start and p.pre[lvl] == 0:
+        lv.restriction(LVL[lvl + 1].r, lv.r, p.quad)
+    else:
+        restriction_res(LVL[lvl + 1].r, lv, lv, p.quad)
+    if lvl + 1 == p.nlevels:
+        MG_kcycle(mg, lvl + 1)              # bottom: smoothing only, no Krylov wrapper around a stationary smoother
+    else:
+        _coarse_gcr(mg, lvl + 1)
+    prolongate_phi(lv.phi, LVL[lvl + 1].phi, lv, p.quad)
+    lv.relax(p.post[lvl])
+
+
+def cycle_once(mg: MG, zero_start: bool = False):
+    """One multigrid cycle of the configured kind on (LVL[0].phi, LVL[0].r): f_MG_ntl, f_MG_simple (V) or the K-cycle.
+    Returns the NTL weights tensor (or None)."""
+    p = mg.p
+    if p.ntl and p.nlevels > 0:
+        return MG_ntl(mg)
+    if p.cycle == "K" and p.nlevels > 0:
+        MG_kcycle(mg, 0, zero_start)
+    else:
+        MG_simple(mg, zero_start)
+    return None
 
 
 def min_res(mg: MG, num_copies: int, level: int) -> torch.Tensor:
@@ -805,10 +881,9 @@ class CycleGraph:
 
     def _body(self):
         mg = self.mg
+        w = cycle_once(mg, self.zero_start)
         if self.ntl:
-            self.weights = MG_ntl(mg)
-        else:
-            MG_simple(mg, self.zero_start)
+            self.weights = w
         if self.with_resmag:
             mg.LVL[0].residue_mag_async()
 
@@ -881,11 +956,9 @@ def _perform_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, 
                     whist[k].copy_(cyc.weights[:8])
                 hist[k].copy_(mg.LVL[0].dots("resmag")[:4])
                 continue
+            a = cycle_once(mg)
             if ntl:
-                a = MG_ntl(mg)
                 whist[k].copy_(a[:8])
-            else:
-                MG_simple(mg)
             d = mg.LVL[0].residue_mag_async()
             hist[k].copy_(d[:4])
         h = hist[:nb].cpu()
@@ -982,10 +1055,7 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         try:
             if not fresh_top:      # (with no pre-smoothing the first write to phi is the overwriting prolongation)
                 pm.ctx.call("mg2d_zero", _ptr(pl0.phi), vs, pm.dcode, st())
-            if ntl:
-                MG_ntl(pm)
-            else:
-                MG_simple(pm, zero_start=True)
+            cycle_once(pm, zero_start=True)
         finally:
             if alias:
                 pl0.phi, pl0.r = keep

@@ -17,7 +17,8 @@ class MGParams:
     mass: float                      # argv[5] "m"; used linearly (it is m^2 for laplace)
     stencil: str = "wilson"          # S6/params.h:68-69
     nlevels: int = 2                 # argv[6]: number of coarse levels; levels are 0..nlevels
-    block: int = 2                   # argv[3]: block_x = block_y
+    block: object = 2                # argv[3]: block_x = block_y; an int, or one block size per coarsening step
+                                     # (S5L/setup.h:2-10 `block_x[level]`: e.g. [4, 2, 2] = 4x4 aggregates on the fine lattice)
     n_smooth: int = 3                # argv[2] num_iters: smoother sweeps per visit
     smoother: str = "gs"             # 'gs' (gs_flag=1, S6/params.h:61) | 'jacobi' (gs_flag=0) | 'mr' (north_star)
                                      # | 'rbgs' (red-black ordering of the GS update)
@@ -38,6 +39,9 @@ class MGParams:
     n_pre: object = None             # pre-smoothing sweeps: int or list per level (default n_smooth, as the reference)
     n_post: object = None            # post-smoothing sweeps: int or list per level (default n_smooth); the coarsest
                                      # level is relaxed once per cycle with n_post (S6/modules_main.h:270-273)
+    cycle: str = "V"                 # 'V' = f_MG_simple (one recursive visit per level) | 'K' = Krylov-accelerated coarse
+                                     # solves (k_inner FGCR steps per coarse level; SURVEY 8f N3, no reference counterpart)
+    k_inner: int = 2
     chiral_transfer: bool = True     # wilson: restriction / prolongation on the chirality-compacted projector
     matrix_free: bool | None = None  # level-0 Wilson operator applied from the links (no D0 stored).
                                      # default: True for smoother 'mr', False for 'gs'/'jacobi' (they need D0)
@@ -49,6 +53,8 @@ class MGParams:
             raise ValueError(f"Incorrect stencil: {self.stencil}. Need either 'laplace' or 'wilson'")
         if self.smoother not in ("gs", "jacobi", "mr", "rbgs"):
             raise ValueError("smoother must be 'gs', 'jacobi', 'mr' or 'rbgs'")
+        if self.cycle not in ("V", "K") or not (1 <= self.k_inner <= 8):
+            raise ValueError("cycle must be 'V' or 'K' with 1 <= k_inner <= 8")
         if self.dtype not in ("complex128", "complex64"):
             raise ValueError("dtype must be complex128 or complex64")
         if self.ntl and self.nlevels < 2:
@@ -57,15 +63,23 @@ class MGParams:
             self.n_null = 2
         n0 = 2 if self.stencil == "wilson" else 1
         self.n_dof_scale = 2 * self.n_null if self.stencil == "wilson" else self.n_null
-        max_levels = math.ceil(math.log2(self.L) / math.log2(self.block)) if self.block > 1 else 0
-        if self.nlevels > max_levels:                                                   # S6/params.h:100-106
-            raise ValueError(f"Too many levels {self.nlevels}. Can only have {max_levels} levels for block size "
-                             f"{self.block} for lattice of size {self.L}")
+        if isinstance(self.block, (list, tuple)):
+            self.blocks = [int(b) for b in self.block]
+            if len(self.blocks) != self.nlevels or any(b < 1 for b in self.blocks):
+                raise ValueError("a per-level block list needs one entry >= 1 per coarsening step (nlevels)")
+            self.block = self.blocks[0] if self.blocks else 1
+        else:
+            self.block = int(self.block)
+            self.blocks = [self.block] * self.nlevels
+            max_levels = math.ceil(math.log2(self.L) / math.log2(self.block)) if self.block > 1 else 0
+            if self.nlevels > max_levels:                                               # S6/params.h:100-106
+                raise ValueError(f"Too many levels {self.nlevels}. Can only have {max_levels} levels for block size "
+                                 f"{self.block} for lattice of size {self.L}")
         self.size, self.n_dof = [self.L], [n0]
-        for _ in range(1, self.nlevels + 1):
-            if self.size[-1] % self.block:
+        for lvl in range(self.nlevels):
+            if self.size[-1] % self.blocks[lvl] or self.size[-1] // self.blocks[lvl] < 1:
                 raise ValueError("lattice size must be divisible by the block size on every level")
-            self.size.append(self.size[-1] // self.block)
+            self.size.append(self.size[-1] // self.blocks[lvl])
             self.n_dof.append(self.n_dof_scale)
         def per_level(v):
             if v is None:

@@ -112,6 +112,12 @@ int mg2d_relax_rb_pm(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_h
                      const void* r, void* cbuf, int cmode, int n, int Lx, int Ly, int colour, int yoff, int dtype,
                      int nvec, long long vstride, long long hstride, const struct mg2d_halo_link* link, void* stream);
 
+/* `nsweeps` full red-black sweeps (both colours) of the pre-multiplied update in ONE cooperative launch, the half sweeps
+ * separated by grid-wide barriers: for the small levels of the hierarchy (whole periodic L x L lattice on this GPU, one
+ * vector) where a half sweep is a latency-bound ~10 us launch.  r == NULL: r = 0. */
+int mg2d_relax_rb_pm_sweeps(mg2d_ctx*, void* phi, const void* M, const void* D0inv, const void* r, void* cbuf,
+                            int n, int L, int nsweeps, int dtype, void* stream);
+
 /* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
  * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64
  * operator); fields and arithmetic stay fp32.  n in {8,16,32}.  Mixed-precision option, no reference counterpart. */

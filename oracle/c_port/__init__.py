@@ -76,7 +76,7 @@ def levels_from_oracle(LVL, p):
 def gcr_solve(LVL, p, b, tol=1e-10, max_iters=1000, restart=8, threads=None, cache=None):
     """Same contract as oracle.mg_oracle.gcr_MG for smoother 'rbgs', quad 1, telescoping cycle.  Returns (x, info).
     cache: a dict that keeps the converted level arrays (-D0^-1 ...) between calls on the same hierarchy."""
-    assert p.smoother == "rbgs" and p.t_flag == 0 and p.quad == 1
+    assert p.smoother == "rbgs" and p.t_flag == 0 and p.quad == 1 and len(set(p.blocks)) <= 1
     levels = None if cache is None else cache.get("levels")
     if levels is None:
         levels = levels_from_oracle(LVL, p)

@@ -66,7 +66,7 @@ def counter_uniform(seed: int, stream: int, start: int, n: int, lo: float = 0.0,
 class Params:
     L: int
     num_iters: int            # smoother sweeps per visit (argv[2])
-    block: int                # block_x = block_y (argv[3])
+    block: object             # block_x = block_y (argv[3]); int, or a list with one block size per coarsening step (ours)
     m: float                  # mass (argv[5]); used linearly
     nlevels: int              # number of coarse levels (argv[6]); levels are 0..nlevels
     t_flag: int = 0           # non-telescoping flag (argv[7])
@@ -84,6 +84,8 @@ class Params:
     min_res_flag: int = 1     # S6/modules_main.h:391
     n_pre: object = None      # ours: per-level pre / post sweep counts (int or list); default num_iters as the reference
     n_post: object = None
+    cycle: str = "V"          # ours: 'K' = Krylov-accelerated coarse solves (k_inner FGCR steps per coarse level)
+    k_inner: int = 2
     size: list = field(default_factory=list)
     n_dof: list = field(default_factory=list)
 
@@ -98,13 +100,18 @@ class Params:
             raise ValueError("Incorrect stencil: need 'laplace' or 'wilson'")
         if self.n_dof_scale is None:
             self.n_dof_scale = scale
-        max_levels = math.ceil(math.log2(self.L) / math.log2(self.block)) if self.block > 1 else 0
-        if self.nlevels > max_levels:
-            raise ValueError("Too many levels")  # S6/params.h:100-106
+        if isinstance(self.block, (list, tuple)):       # ours: per-level block sizes as S5L/setup.h:2-10 `block_x[level]`
+            self.blocks = [int(b) for b in self.block]
+            self.block = self.blocks[0] if self.blocks else 1
+        else:
+            self.blocks = [self.block] * self.nlevels
+            max_levels = math.ceil(math.log2(self.L) / math.log2(self.block)) if self.block > 1 else 0
+            if self.nlevels > max_levels:
+                raise ValueError("Too many levels")  # S6/params.h:100-106
         self.size = [self.L]
         self.n_dof = [n0]
-        for _ in range(1, self.nlevels + 1):
-            self.size.append(self.size[-1] // self.block)
+        for lvl in range(self.nlevels):
+            self.size.append(self.size[-1] // self.blocks[lvl])
             self.n_dof.append(self.n_dof_scale)
         if self.smoother is None:
             self.smoother = "gs" if self.gs_flag == 1 else "jacobi"
@@ -438,13 +445,13 @@ class Level:
 
     # f_block_norm (S6/modules_indiv.h:94-135) applied to every row: f_norm_nn, S6/near_null.h:24-48
     def norm_nn(self, level: int, quad: int, p: Params):
-        agg = aggregates(p.size[level], p.size[level + 1], p.block, quad)
+        agg = aggregates(p.size[level], p.size[level + 1], p.blocks[level], quad)
         for d1 in range(p.n_dof[level + 1]):
             self.phi_null[:, d1, :] = _block_norm(self.phi_null[:, d1, :], agg)
 
     # f_ortho, S6/near_null.h:97-173 (divides by norm, not norm^2: :165)
     def ortho(self, level: int, quad: int, p: Params):
-        agg = aggregates(p.size[level], p.size[level + 1], p.block, quad)
+        agg = aggregates(p.size[level], p.size[level + 1], p.blocks[level], quad)
         P = self.phi_null
         for d1 in range(p.n_dof[level + 1]):
             t = P[:, d1, :].copy()
@@ -460,7 +467,7 @@ class Level:
 
     # f_check_ortho, S6/near_null.h:175-214 -> returns the largest |<null_d1, null_d2>| over aggregates
     def check_ortho(self, level: int, quad: int, p: Params) -> float:
-        agg = aggregates(p.size[level], p.size[level + 1], p.block, quad)
+        agg = aggregates(p.size[level], p.size[level + 1], p.blocks[level], quad)
         Pa = self.phi_null[agg]                               # [Lc^2, b^2, nc, nf]
         G = np.einsum("Xbif,Xbjf->Xij", np.conj(Pa), Pa)
         worst = 0.0
@@ -471,7 +478,7 @@ class Level:
 
     # f_restriction, S6/near_null.h:217-240
     def restriction(self, vec_f: np.ndarray, level: int, p: Params, quad: int) -> np.ndarray:
-        agg = aggregates(p.size[level], p.size[level + 1], p.block, quad)
+        agg = aggregates(p.size[level], p.size[level + 1], p.blocks[level], quad)
         Pv = mv(self.phi_null, vec_f)                         # [Lf^2, nc]
         out = np.zeros((agg.shape[0], self.phi_null.shape[1]), dtype=C128)
         for b in range(agg.shape[1]):
@@ -480,7 +487,7 @@ class Level:
 
     # f_prolongation, S6/near_null.h:242-264: vec_f += P^dagger vec_c   (level = COARSE level index)
     def prolongation(self, vec_f: np.ndarray, vec_c: np.ndarray, level: int, p: Params, quad: int):
-        agg = aggregates(p.size[level - 1], p.size[level], p.block, quad)
+        agg = aggregates(p.size[level - 1], p.size[level], p.blocks[level - 1], quad)
         for b in range(agg.shape[1]):
             s = agg[:, b]
             vec_f[s] += np.einsum("sij,si->sj", np.conj(self.phi_null[s]), vec_c)
@@ -504,7 +511,7 @@ def _block_norm(vec: np.ndarray, agg: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------
 def compute_coarse_matrix(Df: np.ndarray, phi_null: np.ndarray, level: int, quad: int, p: Params) -> np.ndarray:
     """f_compute_coarse_matrix, S6/modules_main.h:81-185.  D_c = P D_f P^dagger."""
-    Lf, Lc, blk = p.size[level], p.size[level + 1], p.block
+    Lf, Lc, blk = p.size[level], p.size[level + 1], p.blocks[level]
     nc = p.n_dof[level + 1]
     agg = aggregates(Lf, Lc, blk, quad)
     xp, xm, yp, ym = neighbours(Lf)
@@ -588,6 +595,59 @@ def MG_simple(LVL, p: Params):
                 prolongate_phi(LVL[lvl - 1].phi, LVL[lvl].phi, LVL[lvl - 1], lvl, p, p.quad)
     else:
         LVL[0].smooth(p.size[0], p.post[0], p)
+
+
+def _coarse_gcr(LVL, p: Params, lvl: int):
+    """K-cycle coarse solve (ours; mirrored 1:1 by the CUDA driver): p.k_inner flexible-GCR steps on D_lvl phi = r_lvl from
+    phi = 0, each preconditioned by MG_kcycle(lvl); classical Gram-Schmidt; fixed step count (no residual test)."""
+    lv, L = LVL[lvl], p.size[lvl]
+    x = np.zeros_like(lv.r)
+    Z, W = [], []
+    keep = lv.phi
+    for _ in range(p.k_inner):
+        lv.phi = np.zeros_like(lv.r)
+        MG_kcycle(LVL, p, lvl)
+        z = lv.phi
+        w = lv.apply_D(z, L)
+        betas = [np.vdot(wj, w) / np.sum(np.abs(wj) ** 2) for wj in W]
+        for zj, wj, beta in zip(Z, W, betas):
+            w = w - beta * wj
+            z = z - beta * zj
+        alpha = np.vdot(w, lv.r) / np.sum(np.abs(w) ** 2)
+        x = x + alpha * z
+        lv.r = lv.r - alpha * w
+        Z.append(z)
+        W.append(w)
+    lv.phi = keep
+    lv.phi[:] = x
+
+
+def MG_kcycle(LVL, p: Params, lvl: int = 0):
+    """One K-cycle on level lvl (ours): f_MG_simple's structure (S6/modules_main.h:255-280) with the single recursive visit
+    of the next level replaced by p.k_inner Krylov steps preconditioned by that level's K-cycle; the coarsest level is only
+    relaxed (as in the reference)."""
+    lv = LVL[lvl]
+    if lvl == p.nlevels:
+        lv.smooth(p.size[lvl], p.post[lvl], p)
+        return
+    lv.smooth(p.size[lvl], p.pre[lvl], p)
+    LVL[lvl + 1].r = restriction_res(lv, lv, lvl, p, p.quad)
+    if lvl + 1 == p.nlevels:
+        MG_kcycle(LVL, p, lvl + 1)
+    else:
+        _coarse_gcr(LVL, p, lvl + 1)
+    prolongate_phi(lv.phi, LVL[lvl + 1].phi, lv, lvl + 1, p, p.quad)
+    lv.smooth(p.size[lvl], p.post[lvl], p)
+
+
+def cycle_once(LVL, NTL, p: Params):
+    if p.t_flag == 1 and p.nlevels > 0:
+        return MG_ntl(LVL, NTL, p)
+    if p.cycle == "K" and p.nlevels > 0:
+        MG_kcycle(LVL, p, 0)
+    else:
+        MG_simple(LVL, p)
+    return None
 
 
 def colpiv_householder_qr_solve(A: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -686,10 +746,9 @@ def perform_MG(LVL, NTL, p: Params, record_phi: bool = False):
     for it in range(p.max_iters):
         if record_phi:
             info["phi_hist"].append(LVL[0].phi.copy())
-        if p.t_flag == 1 and p.nlevels > 0:
-            info["ntl_weights"].append(MG_ntl(LVL, NTL, p))
-        else:
-            MG_simple(LVL, p)
+        w = cycle_once(LVL, NTL, p)
+        if w is not None:
+            info["ntl_weights"].append(w)
         resmag = LVL[0].get_residue_mag(p.size[0])
         info["resnorms"].append(resmag)
         info["iters"] = it + 1
@@ -723,10 +782,7 @@ def gcr_MG(LVL, NTL, p: Params, b: np.ndarray, x0: np.ndarray | None = None, tol
         lv0.r = r.copy()
         for lvl in range(1, p.nlevels + 1):
             LVL[lvl].phi[:] = 0.0
-        if ntl:
-            MG_ntl(LVL, NTL, p)
-        else:
-            MG_simple(LVL, p)
+        cycle_once(LVL, NTL, p)
         z = lv0.phi
         w = lv0.apply_D(z, L0)
         betas = [np.vdot(wj, w) / np.sum(np.abs(wj) ** 2) for wj in W]      # classical Gram-Schmidt: all from the same w

@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
     CK(mg2d_stencil_apply(ctx, dDw, dw, dw + (L - 1) * rown, dw, dD, NULL, n, L, L, MG2D_MODE_APPLY, MG2D_C128, 1, (long long)S * n, (long long)S * n, NULL, NULL));
     CK(mg2d_restrict(ctx, dPw, dw, dP, n, nc, L, L, block, 1, MG2D_C128, NULL));
     /* error behaviour: bad arguments return MG2D_EINVAL and leave a message, they never abort */
-    if (mg2d_restrict(ctx, dPw, dw, dP, n, nc, L, L, 3, 1, MG2D_C128, NULL) != MG2D_EINVAL || strlen(mg2d_last_error(ctx)) == 0) return 1;
+    if (mg2d_restrict(ctx, dPw, dw, dP, n, nc, L, L, 5, 1, MG2D_C128, NULL) != MG2D_EINVAL || strlen(mg2d_last_error(ctx)) == 0) return 1;
     CU(cudaDeviceSynchronize());
     if (mg2d_launch_count(ctx) != 4) { fprintf(stderr, "launch count %d\n", mg2d_launch_count(ctx)); return 1; }
 

@@ -148,6 +148,39 @@ def test_block_stencil_all_sizes(n):
             assert float((Vb[k] - one).abs().max()) < 1e-12 * max(1.0, float(one.abs().max())), (n, nvec, k)
 
 
+@pytest.mark.parametrize("n,L", [(2, 10), (8, 34), (16, 34), (16, 64)])
+def test_persistent_sweeps_kernel(n, L):
+    """mg2d_relax_rb_pm_sweeps (all red-black sweeps of one relax call in ONE cooperative launch, grid barriers between the
+    half sweeps) against the launch-per-half-sweep kernel (bit-identical: same arithmetic order) and the oracle's relax_rb."""
+    rng = np.random.default_rng(100 + n)
+    S = L * L
+    Dref = crand(rng, S, 5, n, n) * 0.2
+    Dref[:, 0] += 3.0 * np.eye(n)
+    lvo = O.Level()
+    lvo.D, lvo.phi, lvo.r = Dref, crand(rng, S, n), crand(rng, S, n)
+    p = mg2d.make_params(L, 0.1, nlevels=0, matrix_free=False)
+    mg = mg2d.MG(p)
+    lv = mg.LVL[0]
+    lv.n, lv.L, lv.S = n, L, S
+    lv.D = mg2d.D_to_reference_layout(T(Dref))
+    for with_r in (True, False):
+        for nsw in (1, 3):
+            o2 = copy.deepcopy(lvo)
+            if not with_r:
+                o2.r = np.zeros_like(o2.r)
+            o2.relax_rb(L, nsw)
+            out = []
+            for persistent in (8192, 0):
+                mg.persistent_sites = persistent
+                phi = T(lvo.phi)
+                n0 = mg.ctx.launches
+                lv.relax(nsw, phi=phi, r=T(lvo.r) if with_r else None, smoother="rbgs")
+                out.append((phi, mg.ctx.launches - n0))
+            assert rel(out[0][0], o2.phi) < 1e-11, (with_r, nsw)
+            assert torch.equal(out[0][0], out[1][0]), (with_r, nsw)
+            assert out[0][1] < out[1][1] or nsw == 1
+
+
 def test_relax_matrix_free_and_batched():
     L = 16
     po, LVLo, _, p, mg, U = _pair(L, 0.02, nlevels=1)

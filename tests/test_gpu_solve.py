@@ -210,6 +210,62 @@ def test_gcr_outer_and_graph():
     assert i1["iters"] == i2["iters"] and float((x1 - x2).abs().max()) < 1e-10
 
 
+def test_kcycle_parity():
+    """K-cycle (2 FGCR steps per coarse level instead of one recursive visit) against the oracle's K-cycle:
+    identical iteration counts and residual histories, stationary and as the preconditioner of the outer FGCR, eager and
+    from the iteration graphs."""
+    L = 32
+    U = O.gauge_gaussian(L, 0.3)
+    b = np.zeros((L * L, 2), dtype=complex)
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    po = O.Params(L=L, num_iters=2, block=2, m=-0.02, nlevels=3, null_iters=40, smoother="rbgs", cycle="K")
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=8)
+    pv = O.Params(L=L, num_iters=2, block=2, m=-0.02, nlevels=3, null_iters=40, smoother="rbgs")
+    LVLv, NTLv = O.build_reference_problem(pv, U)
+    O.compute_near_null(LVLv, NTLv, pv, 1)
+    _, iv = O.gcr_MG(LVLv, NTLv, pv, b, tol=1e-10, restart=8)
+    assert io["iters"] < iv["iters"]                                  # the K-cycle is the stronger preconditioner
+    p = mg2d.make_params(L, -0.02, nlevels=3, n_smooth=2, smoother="rbgs", null_iters=40, cycle="K")
+    mg = mg2d.setup(T(U), p)
+    for use_graph in (False, True):
+        x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=8, use_graph=use_graph)
+        assert ig["iters"] == io["iters"] and hist_close(ig["resnorms"], io["resnorms"], rtol=1e-6)
+        assert ig["true_resnorm"] < 1e-10 and rel(x, xo) < 1e-7
+    # stationary K-cycle iteration (reference-compatible random start)
+    LVLs, NTLs = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLs, NTLs, po, 1)
+    po.res_threshold, po.max_iters = 1e-10, 300
+    is_ = O.perform_MG(LVLs, NTLs, po)
+    m2 = mg2d.setup(T(U), p)
+    x2, i2 = mg2d.solve(m2, tol=1e-10, max_iters=300)
+    assert i2["iters"] == is_["iters"] and hist_close(i2["resnorms"], is_["resnorms"], rtol=1e-6)
+
+
+def test_per_level_block_sizes():
+    """Per-level aggregate sizes (S5L/setup.h:2-10 `block_x[level]`): 4x4 aggregates on the fine lattice, 2x2 above
+    (levels 32/8/4) against the oracle with the same list: coarse operators, iteration count and solution."""
+    L = 32
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
+    po = O.Params(L=L, num_iters=3, block=[4, 2], m=0.0, nlevels=2, null_iters=40, smoother="rbgs", res_threshold=1e-12,
+                  n_dof_scale=8)
+    assert po.size == [32, 8, 4]
+    LVLo, NTLo, io = O.run_reference_flow(po, U)
+    p = mg2d.make_params(L, 0.0, nlevels=2, block=[4, 2], n_null=4, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-12)
+    assert p.size == [32, 8, 4] and p.blocks == [4, 2]
+    mg, ig = mg2d.run_reference_flow(p, T(U))
+    for l in (1, 2):
+        assert rel(mg2d.D_to_reference_layout(mg.LVL[l].D), LVLo[l].D) < 1e-8
+    assert ig["converged"] and ig["iters"] == io["iters"]
+    assert hist_close(ig["resnorms"], io["resnorms"], rtol=1e-6)
+    assert rel(mg.LVL[0].phi, LVLo[0].phi) < 1e-8
+    with pytest.raises(ValueError):
+        mg2d.make_params(L, 0.0, nlevels=2, block=[4])               # one entry per coarsening step
+    with pytest.raises(ValueError):
+        mg2d.make_params(L, 0.0, nlevels=2, block=[3, 2])            # must divide the lattice
+
+
 def test_complex64_and_mixed_precision_solves():
     """complex64 hierarchy (true residual ~1e-6 class) and the mixed-precision solve: complex64 V-cycle inside the
     complex128 FGCR must reach the same 1e-10 TRUE residual (fp64 check) as the all-complex128 solve."""
