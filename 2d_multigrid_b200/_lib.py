@@ -31,6 +31,9 @@ SIGNATURES = {
     "mg2d_premultiply": [_vp, _vp, _vp, _i, _ll, _i, _vp],
     "mg2d_relax_rb_pm": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp, _vp],
     "mg2d_relax_rb_pm_sweeps": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mg2d_hop_factors": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "mg2d_lowrank_pack": [_vp, _vp, _vp, _vp, _i, _i, _ll, _i, _vp],
+    "mg2d_relax_rb_lr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "mg2d_relax_rb_half": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mg2d_to_half": [_vp, _vp, _ll, _vp],
     "mg2d_axpy_ratio2": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _i, _vp],
@@ -82,6 +85,7 @@ PLAIN = {  # entry points without the uniform (ctx, ...) -> int shape
     "mg2d_last_error": ([_vp], C.c_char_p),
     "mg2d_launch_count": ([_vp], _i),
     "mg2d_comm_mailbox_bytes": ([], _i),
+    "mg2d_lowrank_supported": ([_i, _i], _i),
 }
 
 

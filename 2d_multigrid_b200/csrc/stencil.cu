@@ -396,6 +396,204 @@ stencil_rb_pm_sweeps_kernel(cplx<T>* phi, const cplx<T>* __restrict__ M, const c
     }
 }
 
+// ---- low-rank hopping blocks ------------------------------------------------------------------------------------
+// On the first coarse level the hopping block towards direction k is a sum over the R = block fine links that cross the
+// aggregate face, and each fine hopping term has rank one (the spin projector (1 -+ sigma_mu)/2 of the Wilson operator,
+// S6/level.h:155-172; a scalar for the Laplacian): D_k(X) = sum_b a_b b_b^dagger has rank <= R, and so has the
+// pre-multiplied block M_k = -D0^-1 D_k = sum_b (-D0^-1 a_b) b_b^dagger.  For R < N/2 the factors are fewer bytes than the
+// block: 2*4*R*N numbers per site instead of 4*N*N -- half for the 16-dof level over 4x4 aggregates, the level whose
+// sweep dominates the cycle and already runs at the HBM roofline.
+//     t_q  = sum_j conj(b_q)_j phi(s+d_k(q))_j          q = (k-1)*R + b   (stage 1: Q = 4R dot products of length N)
+//     phi(s)_i <- sum_q ma_q,i t_q + c(s)_i             ma_q = -D0^-1 a_q (stage 2)
+// One warp per site.  Storage per site: [Bc: IT x 32][MA: IT x 32] complex, IT = N*R/8, already in lane order:
+//     Bc[t][g] = conj(b_q)_j   with q = g / LP, j = (g % LP)*IT + t,  LP = 32/Q lanes share one dot product
+//     MA[t][g] = ma_q,i        with i = g % N,  q = t*H + g / N,      H = 32/N pair classes
+// so every load is 32 consecutive elements.  (built by mg2d_lowrank_pack from the factors of mg2d_hop_factors)
+template <int N, int R> struct LowRank {
+    static constexpr int Q = 4 * R, IT = N * R / 8, LP = 32 / Q, H = 32 / N, SITE = 64 * IT;
+    static_assert(Q <= 32 && (32 % Q) == 0 && (32 % N) == 0 && N >= 8 && (N * R) % 8 == 0 && LP * IT == N, "unsupported (N, R)");
+};
+
+template <typename T, int N, int R, int CMODE, bool LINK>
+__global__ void __launch_bounds__(ST_THREADS)
+stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ F,
+                     const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, cplx<T>* cbuf, int Lx, int Ly,
+                     int colour, int yoff, HaloLinkDev link) {
+    using C = cplx<T>;
+    using LR = LowRank<N, R>;
+    constexpr int G = 32, GPB = ST_THREADS / G, IT = LR::IT;
+    __shared__ C s_t[GPB][LR::Q];
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N;
+    const int q1 = g / LR::LP, k1 = 1 + q1 / R, j0 = (g % LR::LP) * IT;
+    C* push_lo = nullptr; C* push_hi = nullptr;
+    __shared__ unsigned long long s_epoch;
+    bool waited = false;
+    if (LINK) {
+        if (link.push_next_lo) { push_lo = (C*)link.push_next_lo; push_hi = (C*)link.push_prev_hi; }
+        if (threadIdx.x == 0) s_epoch = link.mine->epoch;
+        __syncthreads();
+    }
+    const int Lh = Lx / 2;
+    const long long S2 = (long long)Lh * Ly;
+    const long long nsteps = (S2 + GPB - 1) / GPB;
+    const long long first_boundary = (Ly >= 2) ? (long long)(Ly - 2) * Lh : 0;      // in the remapped row order
+    for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
+        long long h = step * GPB + grp;
+        const bool active = h < S2;
+        if (!active) h = S2 - 1;
+        int y = (int)(h / Lh);
+        const int xh = (int)(h - (long long)y * Lh);
+        if (LINK) {
+            y = (y + 1 == Ly) ? 0 : y + 1;                                         // rows 1 .. Ly-1, then 0
+            if (link.wait && !waited && step * GPB + GPB - 1 >= first_boundary) {   // CTA-uniform
+                if (threadIdx.x == 0 && !(spin_until(&link.mine->flag_lo, s_epoch) && spin_until(&link.mine->flag_hi, s_epoch)))
+                    atomicExch(&link.mine->error, 1ull);
+                __syncthreads();
+                waited = true;
+            }
+        }
+        const int x = 2 * xh + ((y + yoff + colour) & 1);
+        const size_t s = (size_t)y * Lx + x;
+        const C* Fs = F + s * LR::SITE;
+        C bc[IT], ma[IT];
+#pragma unroll
+        for (int t = 0; t < IT; ++t) bc[t] = __ldg(Fs + 32 * t + g);
+#pragma unroll
+        for (int t = 0; t < IT; ++t) ma[t] = __ldg(Fs + 32 * IT + 32 * t + g);
+        const C* pn = nbr_ptr<C>(phi, lo, hi, k1, x, y, Lx, Ly, N) + j0;
+        C tq = mk<T>(0, 0);
+#pragma unroll
+        for (int t = 0; t < IT; ++t) cfma(tq, bc[t], __ldcg(pn + t));
+#pragma unroll
+        for (int m = 1; m < LR::LP; m <<= 1) tq = cadd(tq, shfl_xor_c(tq, m));
+        if ((g % LR::LP) == 0) s_t[grp][q1] = tq;
+        __syncwarp();
+        C acc = mk<T>(0, 0);
+#pragma unroll
+        for (int t = 0; t < IT; ++t) cfma(acc, ma[t], s_t[grp][t * LR::H + g / N]);
+#pragma unroll
+        for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
+        __syncwarp();
+        if (CMODE == 1) {
+            const C w = __ldg(r + s * N + i);
+            const C c = apply_minus_inv<T, N, G>(Dinv + s * N * N, w, g);       // = -D0^-1 r
+            acc = csub(acc, c);
+            if (active && g < N) cbuf[s * N + i] = mk<T>(-c.x, -c.y);
+        } else if (CMODE == 2) {
+            acc = cadd(acc, __ldg(cbuf + s * N + i));
+        }
+        if (active && g < N) {
+            phi[s * N + i] = acc;
+            if (LINK && push_lo) {
+                if (y == 0) push_hi[(size_t)x * N + i] = acc;
+                if (y + 1 == Ly) push_lo[(size_t)x * N + i] = acc;
+            }
+        }
+    }
+    if (LINK && push_lo) {
+        if (waited || !link.wait) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
+            if (t == (unsigned long long)gridDim.x * gridDim.y - 1ull) {
+                __threadfence_system();
+                link.mine->ticket = 0ull;
+                st_release_sys(&link.next->flag_lo, s_epoch + 1ull);
+                st_release_sys(&link.prev->flag_hi, s_epoch + 1ull);
+                link.mine->epoch = s_epoch + 1ull;
+            }
+        }
+    }
+}
+
+// Factors of the hopping blocks of the first coarse level (see above).  One warp per coarse site; for pair q = (k-1)*R + b
+// the fine link (s -> s' = s + d_k) crossing face k at boundary position b has the hopping block D_k(s) = a v^dagger
+// (rank one: a = the column of largest norm, v^dagger = a^dagger D / |a|^2, checked to 1e-13 -> status bit 4 otherwise);
+//     A[X][q][i] = sum_j P(s)[i][j] a_j ,   B[X][q][i] = sum_j P(s')[i][j] v_j     =>  D_k(X) = sum_b A_q B_q^dagger
+template <typename T>
+__global__ void __launch_bounds__(256)
+hop_factors_kernel(cplx<T>* __restrict__ A, cplx<T>* __restrict__ B, const cplx<T>* __restrict__ Df,
+                   const cplx<T>* __restrict__ P, const cplx<T>* __restrict__ P_lo, const cplx<T>* __restrict__ P_hi,
+                   int nf, int nc, int Lxf, int Lyf, int blk, int* status) {
+    using C = cplx<T>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int Lxc = Lxf / blk, Lyc = Lyf / blk;
+    const long long nagg = (long long)Lxc * Lyc;
+    const int Q = 4 * blk, E = nf * nc;
+    for (long long X = (long long)blockIdx.x * wpb + warp; X < nagg; X += (long long)gridDim.x * wpb) {
+        const int yc = (int)(X / Lxc), xc = (int)(X - (long long)yc * Lxc);
+        for (int q = 0; q < Q; ++q) {
+            const int k = 1 + q / blk, b = q % blk;
+            // boundary site of face k: x1 = blk-1 (k=1), 0 (k=2), y1 = blk-1 (k=3), 0 (k=4); b runs along the face
+            const int x1 = (k == 1) ? blk - 1 : (k == 2) ? 0 : b;
+            const int y1 = (k == 3) ? blk - 1 : (k == 4) ? 0 : b;
+            const int xf = blk * xc + x1, yf = blk * yc + y1;
+            const size_t s = (size_t)yf * Lxf + xf;
+            const C* Ps = P + s * E;
+            const C* Pn;
+            if (k == 1) Pn = P + ((size_t)yf * Lxf + (xf + 1 == Lxf ? 0 : xf + 1)) * E;
+            else if (k == 2) Pn = P + ((size_t)yf * Lxf + (xf == 0 ? Lxf - 1 : xf - 1)) * E;
+            else if (k == 3) Pn = (yf + 1 == Lyf) ? P_hi + (size_t)xf * E : P + ((size_t)(yf + 1) * Lxf + xf) * E;
+            else Pn = (yf == 0) ? P_lo + (size_t)xf * E : P + ((size_t)(yf - 1) * Lxf + xf) * E;
+            const C* Dk = Df + (s * 5 + k) * nf * nf;          // Dk[j*nf + i] = D(i,j)
+            // column of largest norm (every lane computes the same small thing; nf <= 2)
+            int jbest = 0; double best = -1.0;
+            for (int j = 0; j < nf; ++j) {
+                double n2 = 0.0;
+                for (int ii = 0; ii < nf; ++ii) { const C d = Dk[j * nf + ii]; n2 += (double)d.x * d.x + (double)d.y * d.y; }
+                if (n2 > best) { best = n2; jbest = j; }
+            }
+            C a[2], v[2];
+            for (int ii = 0; ii < nf; ++ii) a[ii] = Dk[jbest * nf + ii];
+            double err = 0.0, tot = 0.0;
+            for (int j = 0; j < nf; ++j) {
+                C w = mk<T>(0, 0);                               // a^dagger D[:, j]
+                for (int ii = 0; ii < nf; ++ii) cfmac(w, a[ii], Dk[j * nf + ii]);
+                if (best > 0.0) { w.x = (T)(w.x / best); w.y = (T)(w.y / best); }
+                v[j] = cconj(w);                                 // D(i,j) = a_i conj(v_j)
+                for (int ii = 0; ii < nf; ++ii) {
+                    const C d = Dk[j * nf + ii];
+                    const C rec = cmul(a[ii], w);
+                    err += (double)(d.x - rec.x) * (d.x - rec.x) + (double)(d.y - rec.y) * (d.y - rec.y);
+                    tot += (double)d.x * d.x + (double)d.y * d.y;
+                }
+            }
+            if (lane == 0 && status && err > 1e-26 * tot) atomicOr(status, 4);
+            for (int ic = lane; ic < nc; ic += 32) {
+                C sa = mk<T>(0, 0), sb = mk<T>(0, 0);
+                for (int j = 0; j < nf; ++j) { cfma(sa, Ps[ic * nf + j], a[j]); cfma(sb, Pn[ic * nf + j], v[j]); }
+                A[((size_t)X * Q + q) * nc + ic] = sa;
+                B[((size_t)X * Q + q) * nc + ic] = sb;
+            }
+        }
+    }
+}
+
+// F (lane-ordered factors for stencil_rb_lr_kernel) from A, B and D0^-1:  ma_q = -D0^-1 a_q,  Bc = conj(B).
+template <typename T, int N, int R>
+__global__ void __launch_bounds__(256)
+lowrank_pack_kernel(cplx<T>* __restrict__ F, const cplx<T>* __restrict__ A, const cplx<T>* __restrict__ B,
+                    const cplx<T>* __restrict__ Dinv, long long S) {
+    using C = cplx<T>;
+    using LR = LowRank<N, R>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (long long s = (long long)blockIdx.x * wpb + warp; s < S; s += (long long)gridDim.x * wpb) {
+        const C* As = A + (size_t)s * LR::Q * N;
+        const C* Bs = B + (size_t)s * LR::Q * N;
+        const C* inv = Dinv + (size_t)s * N * N;
+        C* Fs = F + (size_t)s * LR::SITE;
+        for (int t = 0; t < LR::IT; ++t) {
+            const int q = lane / LR::LP, j = (lane % LR::LP) * LR::IT + t;
+            Fs[32 * t + lane] = cconj(Bs[q * N + j]);
+            const int i = lane % N, q2 = t * LR::H + lane / N;
+            C acc = mk<T>(0, 0);
+            for (int l = 0; l < N; ++l) cfma(acc, inv[l * N + i], As[q2 * N + l]);
+            Fs[32 * LR::IT + 32 * t + lane] = mk<T>(-acc.x, -acc.y);
+        }
+    }
+}
+
 // M[s][k-1] = -D0inv[s] D[s][k], k = 1..4 (column-major blocks).  One CTA walks over sites; the site's D0^-1 and
 // the four hopping blocks are staged in shared memory.
 template <typename T, int N>
@@ -776,6 +974,25 @@ int dispatch_rb_pm_sweeps(mg2d_ctx* ctx, int n, void* phi, const void* M, const 
     }
 }
 
+template <typename T, int N, int R>
+int launch_rb_lr(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* F, const void* Dinv, const void* r,
+                 void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, const mg2d_halo_link* link, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / 32;
+    const long long S2 = (long long)(Lx / 2) * Ly;
+    long long nsteps = (S2 + GPB - 1) / GPB;
+    long long cap = (long long)ctx->num_sms * 32;
+    const int gx = (int)(nsteps < cap ? nsteps : cap);
+    const HaloLinkDev ld = make_link(link);
+#define LRK(CM, LK) stencil_rb_lr_kernel<T, N, R, CM, LK><<<gx, ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
+        (const C*)F, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, ld)
+#define LRC(LK) do { if (cmode == 0) LRK(0, LK); else if (cmode == 1) LRK(1, LK); else LRK(2, LK); } while (0)
+    if (link) LRC(true); else LRC(false);
+#undef LRC
+#undef LRK
+    return mg2d_check_launch(ctx, "mg2d_relax_rb_lr");
+}
+
 template <typename T>
 int dispatch_premul(mg2d_ctx* ctx, int n, void* M, const void* D, const void* Dinv, long long S, cudaStream_t st) {
     using C = cplx<T>;
@@ -932,4 +1149,66 @@ extern "C" int mg2d_relax_rb_pm_sweeps(mg2d_ctx* ctx, void* phi, const void* M, 
     if (dtype == MG2D_C128) return dispatch_rb_pm_sweeps<double>(ctx, n, phi, M, D0inv, r, cbuf, L, nsweeps, st);
     if (dtype == MG2D_C64)  return dispatch_rb_pm_sweeps<float>(ctx, n, phi, M, D0inv, r, cbuf, L, nsweeps, st);
     return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_pm_sweeps: bad dtype");
+}
+
+#define MG2D_LR_CASES(CALL) \
+    if (n == 16 && rank == 4) { CALL(16, 4); } \
+    else if (n == 8 && rank == 2) { CALL(8, 2); }
+
+extern "C" int mg2d_lowrank_supported(int n, int rank) {
+    return (n == 16 && rank == 4) || (n == 8 && rank == 2);
+}
+
+extern "C" int mg2d_relax_rb_lr(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* F, const void* D0inv,
+                                const void* r, void* cbuf, int cmode, int n, int rank, int Lx, int Ly, int colour, int yoff,
+                                int dtype, const struct mg2d_halo_link* link, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !F || Lx < 2 || (Lx & 1) || Ly < 1 || cmode < 0 || cmode > 2 || (cmode == 1 && (!r || !D0inv)) ||
+        (cmode != 0 && !cbuf))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_lr: bad argument (Lx must be even)");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_D(N, R) return launch_rb_lr<double, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, link, st)
+#define CALL_F(N, R) return launch_rb_lr<float, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, link, st)
+    if (dtype == MG2D_C128) { MG2D_LR_CASES(CALL_D) }
+    else if (dtype == MG2D_C64) { MG2D_LR_CASES(CALL_F) }
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_lr: bad dtype");
+#undef CALL_D
+#undef CALL_F
+    return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_rb_lr: (n, rank) must be (16,4) or (8,2)");
+}
+
+extern "C" int mg2d_hop_factors(mg2d_ctx* ctx, void* A, void* B, const void* Df, const void* P, const void* P_lo, const void* P_hi,
+                                int nf, int nc, int Lxf, int Lyf, int block, int dtype, int* status, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!A || !B || !Df || !P || !P_lo || !P_hi || nf < 1 || nf > 2 || nc < 1 || block < 1 || Lxf % block || Lyf % block)
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_hop_factors: bad argument (fine n_dof must be 1 or 2)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nagg = (long long)(Lxf / block) * (Lyf / block);
+    long long nb = (nagg + 7) / 8;
+    if (nb > (long long)ctx->num_sms * 16) nb = (long long)ctx->num_sms * 16;
+    if (dtype == MG2D_C128)
+        hop_factors_kernel<double><<<(int)nb, 256, 0, st>>>((cplx<double>*)A, (cplx<double>*)B, (const cplx<double>*)Df, (const cplx<double>*)P,
+                                                            (const cplx<double>*)P_lo, (const cplx<double>*)P_hi, nf, nc, Lxf, Lyf, block, status);
+    else if (dtype == MG2D_C64)
+        hop_factors_kernel<float><<<(int)nb, 256, 0, st>>>((cplx<float>*)A, (cplx<float>*)B, (const cplx<float>*)Df, (const cplx<float>*)P,
+                                                           (const cplx<float>*)P_lo, (const cplx<float>*)P_hi, nf, nc, Lxf, Lyf, block, status);
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_hop_factors: bad dtype");
+    return mg2d_check_launch(ctx, "mg2d_hop_factors");
+}
+
+extern "C" int mg2d_lowrank_pack(mg2d_ctx* ctx, void* F, const void* A, const void* B, const void* D0inv, int n, int rank,
+                                 long long S, int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!F || !A || !B || !D0inv || S < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_lowrank_pack: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long nb = (S + 7) / 8;
+    if (nb > (long long)ctx->num_sms * 16) nb = (long long)ctx->num_sms * 16;
+#define CALL_D(N, R) { lowrank_pack_kernel<double, N, R><<<(int)nb, 256, 0, st>>>((cplx<double>*)F, (const cplx<double>*)A, (const cplx<double>*)B, (const cplx<double>*)D0inv, S); return mg2d_check_launch(ctx, "mg2d_lowrank_pack"); }
+#define CALL_F(N, R) { lowrank_pack_kernel<float, N, R><<<(int)nb, 256, 0, st>>>((cplx<float>*)F, (const cplx<float>*)A, (const cplx<float>*)B, (const cplx<float>*)D0inv, S); return mg2d_check_launch(ctx, "mg2d_lowrank_pack"); }
+    if (dtype == MG2D_C128) { MG2D_LR_CASES(CALL_D) }
+    else if (dtype == MG2D_C64) { MG2D_LR_CASES(CALL_F) }
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_lowrank_pack: bad dtype");
+#undef CALL_D
+#undef CALL_F
+    return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_lowrank_pack: (n, rank) must be (16,4) or (8,2)");
 }

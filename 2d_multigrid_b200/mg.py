@@ -79,6 +79,9 @@ class Level:
         self.D = None          # [S,5,n,n] column-major blocks; None on a matrix-free level 0
         self.D0inv = None
         self.M = None          # [S,4,n,n]: pre-multiplied hopping blocks -D0^-1 D_k of the red-black smoother
+        self.F = None          # low-rank factors of the hopping blocks (first coarse level), lane-ordered for mg2d_relax_rb_lr
+        self.lr_rank = 0       # rank of those factors (= aggregate size of the level below); 0: dense blocks only
+        self._lr_AB = None     # unpacked factors (A, B) until the first sweep needs F
         self.Dh = None         # optional half-precision copies (__half2) of D / D0inv for the complex64 preconditioner
         self.D0inv_h = None
         self.phi_null = None   # [S,nc,nf]
@@ -226,6 +229,8 @@ class Level:
         mg2d_relax_rb_half."""
         if self.D is None or self.mg.p.dtype != "complex64" or self.n not in (8, 16, 32):
             return
+        if self.lr_rank and self.mg.lowrank:      # complex64 low-rank factors are already fewer bytes than half-precision blocks
+            return
         self._ensure_D0inv()
         mg = self.mg
         self.Dh = torch.empty(self.D.shape, dtype=torch.float32, device=mg.device)            # 4 bytes per complex
@@ -246,6 +251,30 @@ class Level:
             self._ensure_D0inv()
             self.M = torch.empty((self.S, 4, self.n, self.n), dtype=self.mg.tdtype, device=self.mg.device)
             self.mg.ctx.call("mg2d_premultiply", _ptr(self.M), _ptr(self.D), _ptr(self.D0inv), self.n, self.S, self.mg.dcode, _stream())
+
+    def _ensure_F(self):
+        """Lane-ordered low-rank factors (conj(B), -D0^-1 A) of the hopping blocks for mg2d_relax_rb_lr."""
+        if self.F is None and self._lr_AB is not None:
+            self._ensure_D0inv()
+            A, B = self._lr_AB
+            self.F = torch.empty((self.S, 2, self.n * self.lr_rank // 8, 32), dtype=self.mg.tdtype, device=self.mg.device)
+            self.mg.ctx.call("mg2d_lowrank_pack", _ptr(self.F), _ptr(A), _ptr(B), _ptr(self.D0inv), self.n, self.lr_rank, self.S,
+                             self.mg.dcode, _stream())
+            self._lr_AB = None
+        if self.F is not None:
+            self._ensure_D0inv()       # (a precision copy receives F but builds its own D0^-1 for the c = D0^-1 r pass)
+        return self.F is not None
+
+    def hop_factors(self, lvl_f: "Level", P: torch.Tensor, p_lo: int, p_hi: int):
+        """Rank-`block` factors of this level's hopping blocks from the fine operator and projector (mg2d_hop_factors);
+        `self` is the coarse level.  status[1] != 0 (a fine hopping block that is not rank one) is read by the caller."""
+        mg = self.mg
+        Q = 4 * lvl_f.block
+        A = torch.empty((self.S, Q, self.n), dtype=mg.tdtype, device=mg.device)
+        B = torch.empty_like(A)
+        mg.ctx.call("mg2d_hop_factors", _ptr(A), _ptr(B), _ptr(lvl_f.D), _ptr(P), p_lo, p_hi, lvl_f.n, self.n, lvl_f.L, lvl_f.Ly,
+                    lvl_f.block, mg.dcode, _ptr(mg.status[1:]), _stream())
+        self._lr_AB, self.F, self.lr_rank = (A, B), None, lvl_f.block
 
     def relax(self, num_iter: int, gs_flag: int | None = None, phi=None, r="self", smoother: str | None = None):
         """f_relax (S6/level.h:100-128).  gs_flag 1 = lexicographic Gauss-Seidel, 0 = Jacobi (reference);
@@ -332,6 +361,22 @@ class Level:
                             lo, hi = self._halo(ph)
                             mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(rv),
                                         float(mg.p.mass), self.L, self.Ly, colour, self.y0 & 1, mg.dcode, _stream())
+                    elif self.lr_rank and nvec == 1 and mg.premul and mg.lowrank and self._ensure_F():
+                        # first coarse level: rank-`block` factors of the pre-multiplied hopping blocks (half the bytes)
+                        cmode = 0 if r is None else (1 if it == 0 else 2)
+                        cbuf = None if r is None else self.work("pm_c")
+                        link = None
+                        if self.distributed and mg.comm.fused:
+                            k = 2 * it + colour
+                            if k == 0:
+                                self._halo(phi)
+                            lk, lo, hi = mg.comm.fused_link(phi, self.L, self.Ly, self.n, 1, (self.lvl, self.n, 1, 1), 1, k,
+                                                            push=(k < 2 * num_iter - 1))
+                            link = ctypes.byref(lk)
+                        else:
+                            lo, hi = self._halo(phi)
+                        mg.ctx.call("mg2d_relax_rb_lr", _ptr(phi), lo, hi, _ptr(self.F), _ptr(self.D0inv), _ptr(r), _ptr(cbuf), cmode,
+                                    self.n, self.lr_rank, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, link, _stream())
                     elif self.Dh is not None and nvec == 1 and mg.use_half:
                         lo, hi = self._halo(phi)
                         mg.ctx.call("mg2d_relax_rb_half", _ptr(phi), lo, hi, _ptr(self.Dh), _ptr(self.D0inv_h), _ptr(r),
@@ -506,6 +551,7 @@ class MG:
         self.info = {}
         self.use_half = False      # complex64 preconditioner copy: smooth with the half-precision operator blocks
         self.premul = True         # red-black sweeps on stored operators use the pre-multiplied blocks -D0^-1 D_k
+        self.lowrank = True        # first coarse level: red-black sweeps stream rank-`block` factors of the hopping blocks
         self.persistent_sites = 8192   # levels with at most this many sites relax all sweeps of a call in one cooperative launch
         self.two_colour = True     # level-0 matrix-free red-black sweeps through the one-pass two-colour kernel
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
@@ -542,7 +588,7 @@ class MG:
         """Drop every device buffer and break the Level <-> MG reference cycles so that the memory returns to the
         allocator immediately (hierarchies are tens of GB)."""
         for lv in self.LVL + [nt for row in self.NTL for nt in row]:
-            lv.__dict__.update(phi=None, r=None, D=None, D0inv=None, M=None, Dh=None, D0inv_h=None, phi_null=None, phi_null_c=None,
+            lv.__dict__.update(phi=None, r=None, D=None, D0inv=None, M=None, F=None, _lr_AB=None, Dh=None, D0inv_h=None, phi_null=None, phi_null_c=None,
                                U=None, _U_halos=None, _work={}, mg=None)
         for v in list(self.info.values()):
             if isinstance(v, MG):
@@ -613,6 +659,8 @@ def make_single_precision(mg: "MG") -> "MG":
             l32.phi_null = lv.phi_null.to(c64)
         if lv.D is not None:
             l32.D = lv.D.to(c64)
+        if lv.lr_rank and mg.lowrank and lv._ensure_F():
+            l32.F, l32.lr_rank = lv.F.to(c64), lv.lr_rank
         l32.matrix_free = lv.matrix_free
         if lv.U is not None:
             l32.U = lv.U.to(c64)
@@ -648,8 +696,12 @@ def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
     lvl_c.D = torch.empty((lvl_c.S, 5, nc, nc), dtype=mg.tdtype, device=mg.device)
     lvl_c.D0inv = None
     lvl_c.M = None
+    lvl_c.F, lvl_c._lr_AB, lvl_c.lr_rank = None, None, 0
     P = lvl_P.phi_null
     p_lo, p_hi = lvl_f._halo(P, 1, nc * nf)          # projector rows below / above the strip (or the periodic wrap)
+    if (mg.lowrank and nf <= 2 and quad == 1 and lvl_P is lvl_f and lvl_c.Ly * lvl_f.block == lvl_f.Ly
+            and 2 * lvl_f.block < nc and mg.ctx.lib.mg2d_lowrank_supported(nc, lvl_f.block)):
+        lvl_c.hop_factors(lvl_f, P, p_lo, p_hi)
     if lvl_f.distributed and not lvl_c.distributed:
         # first replicated level: every rank builds its strip of D_c, then the strips are all-gathered
         blk = lvl_f.block
@@ -689,6 +741,13 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
     if mg.comm is not None:
         mg.comm.allreduce(mg.status, "max")
     st = mg.status.cpu()
+    if int(st[1]) != 0:       # a fine hopping block that is not rank one: keep the dense blocks
+        for lv in mg.LVL:
+            lv.F, lv._lr_AB, lv.lr_rank = None, None, 0
+        mg.status[1] = 0
+    for lv in mg.LVL:
+        if lv.lr_rank and lv.M is not None and lv._ensure_F():
+            lv.M = None       # the dense pre-multiplied blocks were only needed by the batched near-null relaxation
     if int(st[0]) != 0:
         raise FloatingPointError(f"near-null orthonormalisation failed (status {int(st[0])}): NaN or tiny norm "
                                  "(S6/modules_indiv.h:119-126, S6/near_null.h:149-159)")
@@ -1075,7 +1134,7 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
 
     graphs = None
     if use_graph and pm.p.smoother != "gs":
-        gkey = ("iter_graphs", id(pm), pm.use_half, restart, tuple(pm.p.pre), tuple(pm.p.post))
+        gkey = ("iter_graphs", id(pm), pm.use_half, pm.lowrank, pm.premul, pm.persistent_sites, restart, tuple(pm.p.pre), tuple(pm.p.post))
         graphs = mg.info.setdefault(gkey, {})
     info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
     bn2 = None

@@ -118,6 +118,25 @@ int mg2d_relax_rb_pm(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_h
 int mg2d_relax_rb_pm_sweeps(mg2d_ctx*, void* phi, const void* M, const void* D0inv, const void* r, void* cbuf,
                             int n, int L, int nsweeps, int dtype, void* stream);
 
+/* Low-rank hopping blocks of the FIRST coarse level (no reference counterpart in storage; same update as f_relax,
+ * S6/level.h:100-128).  Every fine hopping term has rank one (Wilson spin projector (1 -+ sigma_mu)/2, S6/level.h:155-172;
+ * a scalar for the Laplacian) and only `block` fine links cross an aggregate face, so the Galerkin hopping block
+ * (S6/modules_main.h:148-155) is D_k(X) = sum_{b<block} A_q B_q^dagger, q = (k-1)*block + b: rank <= block.
+ *   mg2d_hop_factors   A, B [Sc][4*block][nc] from the fine operator Df (n_dof 1 or 2) and the projector P (+ halo rows);
+ *                      *status |= 4 when a fine hopping block is not rank one to 1e-13 (the caller then keeps dense blocks)
+ *   mg2d_lowrank_pack  F[s][2][n*rank/8][32]: conj(B) and -D0inv A in the lane order of the sweep kernel
+ *   mg2d_relax_rb_lr   the red-black half sweep of mg2d_relax_rb_pm (same cmode / link meaning, one vector) streaming
+ *                      2*4*rank*n numbers per site instead of 4*n*n.  (n, rank) in {(16,4), (8,2)}: 8 null vectors over
+ *                      4x4 aggregates, 4 over 2x2 (wilson); 16 over 4x4 (laplace). */
+int mg2d_lowrank_supported(int n, int rank);
+int mg2d_hop_factors(mg2d_ctx*, void* A, void* B, const void* Df, const void* P, const void* P_lo, const void* P_hi,
+                     int nf, int nc, int Lxf, int Lyf, int block, int dtype, int* status, void* stream);
+int mg2d_lowrank_pack(mg2d_ctx*, void* F, const void* A, const void* B, const void* D0inv, int n, int rank,
+                      long long nsites, int dtype, void* stream);
+int mg2d_relax_rb_lr(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* F, const void* D0inv,
+                     const void* r, void* cbuf, int cmode, int n, int rank, int Lx, int Ly, int colour, int yoff,
+                     int dtype, const struct mg2d_halo_link* link, void* stream);
+
 /* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
  * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64
  * operator); fields and arithmetic stay fp32.  n in {8,16,32}.  Mixed-precision option, no reference counterpart. */

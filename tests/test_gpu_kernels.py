@@ -249,6 +249,62 @@ def test_setup_and_transfer(stencil, block, n_null):
         assert float((c1 - c2).abs().max()) < 1e-11
 
 
+@pytest.mark.parametrize("stencil,block,n_null", [("wilson", 4, 8), ("wilson", 2, 4), ("laplace", 4, 16)])
+def test_lowrank_hop_factors_and_sweep(stencil, block, n_null):
+    """First coarse level: the Galerkin hopping blocks (S6/modules_main.h:148-155) have rank <= block because every fine
+    hopping term has rank one (S6/level.h:139-172).  mg2d_hop_factors must reproduce the dense blocks of
+    mg2d_coarse_matrix (sum_b A_q B_q^dagger = D_k), and the red-black sweep on the packed factors (mg2d_relax_rb_lr) must
+    equal the oracle's relax_rb and the dense pre-multiplied kernel, with and without a right-hand side."""
+    L = 16
+    rng = np.random.default_rng(8)
+    po, LVLo, NTLo, p, mg, U = _pair(L, 0.05, stencil=stencil, nlevels=1, block=block, n_null=n_null)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    mg.persistent_sites = 0
+    lv = mg.LVL[1]
+    P = mg.LVL[0].phi_null
+    mg2d.compute_near_null(mg)
+    assert lv.lr_rank == block and int(mg.status[1].item()) == 0
+    # factors (recomputed here: compute_near_null already packed and dropped them)
+    p_lo, p_hi = mg.LVL[0]._halo(mg.LVL[0].phi_null, 1, lv.n * mg.LVL[0].n)
+    lv.hop_factors(mg.LVL[0], mg.LVL[0].phi_null, p_lo, p_hi)
+    A, B = lv._lr_AB
+    Sc, nc = lv.S, lv.n
+    A4, B4 = A.reshape(Sc, 4, block, nc), B.reshape(Sc, 4, block, nc)
+    rec = torch.einsum("skbi,skbj->skij", A4, B4.conj())
+    assert rel(rec, LVLo[1].D[:, 1:]) < 1e-10
+    assert rel(rec, mg2d.D_to_reference_layout(lv.D)[:, 1:].cpu().numpy()) < 1e-13
+    lv.F = None
+    assert lv._ensure_F() and lv._lr_AB is None
+    for with_r in (True, False):
+        phi0, r0 = crand(rng, Sc, nc), crand(rng, Sc, nc)
+        o2 = copy.deepcopy(LVLo[1])
+        o2.phi, o2.r = phi0.copy(), (r0.copy() if with_r else np.zeros_like(r0))
+        o2.relax_rb(po.size[1], 3)
+        out = {}
+        for lowrank in (True, False):
+            mg.lowrank = lowrank
+            phi = T(phi0)
+            lv.relax(3, phi=phi, r=T(r0) if with_r else None, smoother="rbgs")
+            out[lowrank] = phi
+        mg.lowrank = True
+        assert rel(out[True], o2.phi) < 1e-11 and rel(out[False], o2.phi) < 1e-11
+        assert float((out[True] - out[False]).abs().max()) < 1e-12 * float(out[False].abs().max())
+    assert lv.M is not None         # the dense path above rebuilt its blocks lazily
+
+
+def test_lowrank_not_used_when_fine_hops_are_not_rank_one():
+    """A fine operator whose hopping blocks have full rank (random 2x2 blocks): mg2d_hop_factors flags it and the setup
+    keeps the dense blocks."""
+    L = 16
+    rng = np.random.default_rng(9)
+    po, LVLo, NTLo, p, mg, U = _pair(L, 0.05, nlevels=1, block=4, n_null=8)
+    D = crand(rng, L * L, 5, 2, 2) * 0.2
+    D[:, 0] += 3.0 * np.eye(2)
+    mg.LVL[0].D = T(D)
+    mg2d.compute_near_null(mg)
+    assert mg.LVL[1].lr_rank == 0 and mg.LVL[1].F is None and int(mg.status[1].item()) == 0
+
+
 def test_minres_pieces():
     """Gram matrix (mg2d_cdot_batch), column-pivoted QR solve (mg2d_minres_solve), f_scale_phi."""
     rng = np.random.default_rng(6)

@@ -185,6 +185,41 @@ def test_v04_cycle_chiral_transfer_parity(post):
     assert float((f3 - (f1 - vf)).abs().max()) < 1e-13
 
 
+def test_lowrank_level1_solve_parity():
+    """The bench cycle with the level-1 sweeps on the rank-4 factors of the hopping blocks (mg2d_relax_rb_lr): same
+    iteration count, residual history and solution as the oracle (dense blocks) and as the dense GPU path, eager and from
+    the iteration graphs, complex128 and with the complex64 preconditioner copy."""
+    L = 64
+    U = O.gauge_from_phases(O.gauge_quenched_phases(L, 6.0, sweeps=30))
+    b = np.zeros((L * L, 2), dtype=complex)
+    b[L // 2 + (L // 2) * L, 0] = 1.0
+    po = O.Params(L=L, num_iters=4, n_pre=0, n_post=[4, 2, 8], block=4, m=-0.02, nlevels=2, null_iters=40, smoother="rbgs", n_dof_scale=16)
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=8)
+    p = mg2d.make_params(L, -0.02, nlevels=2, block=4, n_null=8, n_smooth=4, n_pre=0, n_post=[4, 2, 8], smoother="rbgs", null_iters=40)
+    mg = mg2d.MG(p)
+    mg.persistent_sites = 0                     # (16^2 sites would otherwise take the one-launch dense path)
+    mg.init_reference_fields()
+    mg.set_gauge(T(U))
+    mg2d.compute_near_null(mg)
+    assert mg.LVL[1].lr_rank == 4 and mg.LVL[1].F is not None and mg.LVL[2].lr_rank == 0
+    res = {}
+    for lowrank in (True, False):
+        mg.lowrank = lowrank
+        for use_graph in (False, True):
+            x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=8, use_graph=use_graph)
+            assert ig["iters"] == io["iters"] and ig["true_resnorm"] < 1e-10
+            assert hist_close(ig["resnorms"], io["resnorms"], rtol=1e-6)
+            assert rel(x, xo) < 1e-7
+            res[(lowrank, use_graph)] = x.clone()
+    assert float((res[(True, False)] - res[(False, False)]).abs().max()) < 1e-9 * float(res[(False, False)].abs().max())
+    mg.lowrank = True
+    x32, i32 = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=8, precond_dtype="complex64")
+    assert mg.info["single"].LVL[1].F is not None and mg.info["single"].LVL[1].F.dtype == torch.complex64
+    assert i32["true_resnorm"] < 1e-10 and abs(i32["iters"] - io["iters"]) <= 1 and rel(x32, xo) < 1e-7
+
+
 def test_gcr_outer_and_graph():
     L = 32
     U = O.gauge_gaussian(L, 0.3)
@@ -288,11 +323,13 @@ def test_complex64_and_mixed_precision_solves():
     mg16 = mg2d.setup(U, p16)
     xa, ia = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr")
     xh, ih = mg2d.solve(mg16, rhs=b, tol=1e-10, outer="gcr", precond_dtype="complex64+half")
-    assert mg16.info["single"].LVL[1].Dh is not None and mg16.info["single"].use_half
+    sh = mg16.info["single"]
+    # level 1 streams its complex64 low-rank factors (fewer bytes than half-precision dense blocks), level 2 the half blocks
+    assert sh.LVL[1].Dh is None and sh.LVL[1].F is not None and sh.LVL[2].Dh is not None and sh.use_half
     assert ih["converged"] and ih["true_resnorm"] < 1e-10 and abs(ih["iters"] - ia["iters"]) <= 3
     assert float((xh - xa).abs().max()) < 1e-8
     # the half kernel itself against the complex64 kernel on the same data (difference = half rounding of D only)
-    l1 = mg16.info["single"].LVL[1]
+    l1 = sh.LVL[2]
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     ph = torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64)
     l1.r.copy_(torch.randn((l1.S, l1.n), generator=g, dtype=torch.float32, device="cuda").to(torch.complex64))
