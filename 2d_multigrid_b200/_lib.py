@@ -40,6 +40,8 @@ SIGNATURES = {
     "mg2d_gcr_dots": [_vp, _ll, _i, _vp, _ll, _i, _vp, _vp],
     "mg2d_gcr_ortho": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _vp],
     "mg2d_gcr_step": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp],
+    "mg2d_gcr_step_lazy": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _vp, _vp],
+    "mg2d_gcr_xupdate": [_vp, _vp, _ll, _i, _vp, _ll, _i, _vp],
     "mg2d_mr_update": [_vp, _vp, _vp, _vp, _d, _ll, _i, _i, _ll, _vp],
     "mg2d_axpy": [_vp, _vp, _d, _d, _vp, _ll, _i, _vp],
     "mg2d_zero": [_vp, _ll, _i, _vp],

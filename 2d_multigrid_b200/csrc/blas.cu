@@ -417,15 +417,23 @@ gcr_ortho_kernel(cplx<T>* __restrict__ w, cplx<T>* __restrict__ z, const cplx<T>
     }
     double red[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        C wv = w[e], zv = z[e];
+        C wv = w[e];
+        if (z) {
+            C zv = z[e];
 #pragma unroll
-        for (int j = 0; j < GCR_MAXJ; ++j) {
-            if (j < nj) {
-                cfma(wv, beta[j], __ldg(W + (size_t)j * stride + e));
-                cfma(zv, beta[j], __ldg(Z + (size_t)j * stride + e));
+            for (int j = 0; j < GCR_MAXJ; ++j) {
+                if (j < nj) {
+                    cfma(wv, beta[j], __ldg(W + (size_t)j * stride + e));
+                    cfma(zv, beta[j], __ldg(Z + (size_t)j * stride + e));
+                }
             }
+            z[e] = zv;
+        } else {                                   // lazy variant: the preconditioned directions stay raw (see gcr_step_lazy_kernel)
+#pragma unroll
+            for (int j = 0; j < GCR_MAXJ; ++j)
+                if (j < nj) cfma(wv, beta[j], __ldg(W + (size_t)j * stride + e));
         }
-        w[e] = wv; z[e] = zv;
+        w[e] = wv;
         const C rv = __ldg(r + e);
         red[0] += (double)wv.x * wv.x + (double)wv.y * wv.y;
         red[1] += (double)wv.x * rv.x + (double)wv.y * rv.y;       // <w, r> = conj(w) r
@@ -454,7 +462,95 @@ gcr_step_kernel(cplx<T>* __restrict__ x, cplx<T>* __restrict__ r, const cplx<T>*
     }
     grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
+// Lazy solution update.  With zh_j = z_j - sum_{i<j} b_ij zh_i (what gcr_ortho_kernel does to z when it is given one) the
+// orthogonalised direction is a combination zh_j = sum_{i<=j} c_ij z_i of the RAW preconditioned residuals, c_.j = e_j -
+// sum_{i<j} b_ij c_.i, and the solution after the cycle is x + sum_i g_i z_i with g_i = sum_j a_j c_ij.  The 8 x 8
+// recursion runs in one thread; the vectors z_i are then never rewritten and x is touched once per restart cycle
+// (gcr_xupdate_kernel) instead of every iteration: (2j+9) instead of (3j+14) vector passes in iteration j of a cycle.
+// coef (doubles): c[i][j] at 2*(8*i+j), g[i] at 128 + 2*i.
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_step_lazy_kernel(cplx<T>* __restrict__ r, const cplx<T>* __restrict__ w, const double* __restrict__ wr,
+                     double* __restrict__ wn2_slot, const double* __restrict__ dots, const double* __restrict__ wn2, int nj,
+                     double* __restrict__ coef, long long n, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                     double* __restrict__ out, XComm* xc) {
+    using C = cplx<T>;
+    const double d = wr[0];
+    const double ar = d > 0.0 ? wr[1] / d : 0.0, ai = d > 0.0 ? wr[2] / d : 0.0;
+    const C na = mk<T>((T)-ar, (T)-ai);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *wn2_slot = d;
+        double cr[GCR_MAXJ], ci[GCR_MAXJ];
+        for (int i = 0; i < GCR_MAXJ; ++i) { cr[i] = (i == nj) ? 1.0 : 0.0; ci[i] = 0.0; }
+        for (int i = 0; i < nj; ++i) {
+            const double di = wn2[i];
+            const double br = di > 0.0 ? dots[2 * i] / di : 0.0, bi = di > 0.0 ? dots[2 * i + 1] / di : 0.0;
+            for (int l = 0; l <= i; ++l) {                       // c_.j -= b_ij c_.i  (column i has entries l <= i)
+                const double xr = coef[2 * (8 * l + i)], xi = coef[2 * (8 * l + i) + 1];
+                cr[l] -= br * xr - bi * xi;
+                ci[l] -= br * xi + bi * xr;
+            }
+        }
+        for (int l = 0; l < GCR_MAXJ; ++l) {
+            coef[2 * (8 * l + nj)] = cr[l]; coef[2 * (8 * l + nj) + 1] = ci[l];
+            const double gr = (nj == 0) ? 0.0 : coef[128 + 2 * l], gi = (nj == 0) ? 0.0 : coef[128 + 2 * l + 1];
+            coef[128 + 2 * l] = gr + (ar * cr[l] - ai * ci[l]);
+            coef[128 + 2 * l + 1] = gi + (ar * ci[l] + ai * cr[l]);
+        }
+    }
+    double red[1] = {0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C rv = r[e];
+        cfma(rv, na, __ldg(w + e));
+        r[e] = rv;
+        red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+    }
+    grid_reduce<1, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_xupdate_kernel(cplx<T>* __restrict__ x, const cplx<T>* __restrict__ Z, long long stride, int nj,
+                   const double* __restrict__ coef, long long n) {
+    using C = cplx<T>;
+    C g[GCR_MAXJ];
+#pragma unroll
+    for (int j = 0; j < GCR_MAXJ; ++j) g[j] = (j < nj) ? mk<T>((T)coef[128 + 2 * j], (T)coef[128 + 2 * j + 1]) : mk<T>(0, 0);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        C xv = x[e];
+#pragma unroll
+        for (int j = 0; j < GCR_MAXJ; ++j)
+            if (j < nj) cfma(xv, g[j], __ldg(Z + (size_t)j * stride + e));
+        x[e] = xv;
+    }
+}
 }  // namespace
+
+extern "C" int mg2d_gcr_step_lazy(mg2d_ctx* ctx, void* r, const void* w, const double* wr, double* wn2_slot, const double* dots,
+                                  const double* wn2, int nj, double* coef, long long nelem, int dtype, double* out, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!r || !w || !wr || !wn2_slot || !coef || !out || nelem < 1 || nj < 0 || nj >= GCR_MAXJ || (nj > 0 && (!dots || !wn2)))
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_step_lazy: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
+    DISPATCH_T(dtype,
+        (gcr_step_lazy_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)r, (const double2*)w, wr, wn2_slot, dots, wn2, nj, coef, nelem, ctx->partials, ctx->counter, out, xc)),
+        (gcr_step_lazy_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)r, (const float2*)w, wr, wn2_slot, dots, wn2, nj, coef, nelem, ctx->partials, ctx->counter, out, xc)),
+        "mg2d_gcr_step_lazy");
+}
+
+extern "C" int mg2d_gcr_xupdate(mg2d_ctx* ctx, void* x, const void* Z, long long stride, int nj, const double* coef, long long nelem,
+                                int dtype, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!x || !Z || !coef || nelem < 1 || nj < 1 || nj > GCR_MAXJ) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_xupdate: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(ctx, nelem);
+    DISPATCH_T(dtype,
+        (gcr_xupdate_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)x, (const double2*)Z, stride, nj, coef, nelem)),
+        (gcr_xupdate_kernel<float><<<grid, BL_THREADS, 0, st>>>((float2*)x, (const float2*)Z, stride, nj, coef, nelem)),
+        "mg2d_gcr_xupdate");
+}
 
 extern "C" int mg2d_gcr_dots(mg2d_ctx* ctx, const void* W, long long stride, int nj, const void* w, long long nelem, int dtype,
                              double* out, void* stream) {
@@ -472,7 +568,7 @@ extern "C" int mg2d_gcr_dots(mg2d_ctx* ctx, const void* W, long long stride, int
 extern "C" int mg2d_gcr_ortho(mg2d_ctx* ctx, void* w, void* z, const void* r, const void* W, const void* Z, long long stride, int nj,
                               const double* dots, const double* wn2, long long nelem, int dtype, double* out, void* stream) {
     if (!ctx) return MG2D_EINVAL;
-    if (!w || !z || !r || !out || nj < 0 || nj > GCR_MAXJ || nelem < 1 || (nj > 0 && (!W || !Z || !dots || !wn2)))
+    if (!w || !r || !out || nj < 0 || nj > GCR_MAXJ || nelem < 1 || (nj > 0 && (!W || (z && !Z) || !dots || !wn2)))
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_ortho: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);

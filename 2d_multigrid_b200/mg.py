@@ -552,6 +552,7 @@ class MG:
         self.use_half = False      # complex64 preconditioner copy: smooth with the half-precision operator blocks
         self.premul = True         # red-black sweeps on stored operators use the pre-multiplied blocks -D0^-1 D_k
         self.lowrank = True        # first coarse level: red-black sweeps stream rank-`block` factors of the hopping blocks
+        self.lazy_gcr = True       # outer FGCR: raw stored directions + one solution update per restart cycle (mg2d_gcr_step_lazy)
         self.persistent_sites = 8192   # levels with at most this many sites relax all sweeps of a call in one cooperative launch
         self.two_colour = True     # level-0 matrix-free red-black sweeps through the one-pass two-colour kernel
         self.comm = None           # set by dist.DistMG: strip decomposition over torch.distributed (NCCL)
@@ -1089,6 +1090,8 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
     x, b = lv0.work("gcr_x"), lv0.work("gcr_b")
     r = lv0.work("gcr_r")
     Z, W = lv0.work("gcr_Z", restart), lv0.work("gcr_W", restart)
+    lazy = bool(mg.lazy_gcr)
+    coef = lv0.dots("gcr_coef")     # lazy update: coefficients of the orthogonalised directions in the raw z_i (mg2d_gcr_step_lazy)
     sc = lv0.dots("gcr")            # [0:4] |w|^2,<w,r> ; [4] |r|^2 ; [5] |b|^2 ; [16:32] <W_j,w> ; [40+j] |w_j|^2 ; [48+j] |r|^2 after slot j
     call("mg2d_copy", _ptr(x), _ptr(lv0.phi), vs, dc, st())
     call("mg2d_copy", _ptr(b), _ptr(lv0.r), vs, dc, st())
@@ -1125,6 +1128,17 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         if slot > 0:
             with lv0.global_sums(sc[16:16 + 2 * slot]):
                 call("mg2d_gcr_dots", _ptr(W), vs, slot, _ptr(w), vs, dc, _ptr(sc[16:]), st())
+        if lazy:
+            # the z_i stay raw and x is updated once per restart cycle: (2j+9) instead of (3j+14) vector passes
+            with lv0.global_sums(sc[0:4]):
+                call("mg2d_gcr_ortho", _ptr(w), None, _ptr(r), _ptr(W), None, vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
+                     vs, dc, _ptr(sc[0:]), st())
+            with lv0.global_sums(sc[48 + slot:49 + slot]):
+                call("mg2d_gcr_step_lazy", _ptr(r), _ptr(w), _ptr(sc[0:]), _ptr(sc[40 + slot:]), _ptr(sc[16:]), _ptr(sc[40:]), slot,
+                     _ptr(coef), vs, dc, _ptr(sc[48 + slot:]), st())
+            if slot == restart - 1:
+                call("mg2d_gcr_xupdate", _ptr(x), _ptr(Z), vs, restart, _ptr(coef), vs, dc, st())
+            return
         with lv0.global_sums(sc[0:4]):
             call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(r), _ptr(W), _ptr(Z), vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
                  vs, dc, _ptr(sc[0:]), st())
@@ -1134,11 +1148,11 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
 
     graphs = None
     if use_graph and pm.p.smoother != "gs":
-        gkey = ("iter_graphs", id(pm), pm.use_half, pm.lowrank, pm.premul, pm.persistent_sites, restart, tuple(pm.p.pre), tuple(pm.p.post))
+        gkey = ("iter_graphs", id(pm), lazy, pm.use_half, pm.lowrank, pm.premul, pm.persistent_sites, restart, tuple(pm.p.pre), tuple(pm.p.post))
         graphs = mg.info.setdefault(gkey, {})
     info = {"iters": 0, "resnorms": [], "ntl_weights": [], "converged": False, "diverged": False}
     bn2 = None
-    it, slot = 0, 0
+    it, slot, pending = 0, 0, 0
     done = False
     while it < max_iters and not done:
         nb = min(check_every, max_iters - it, restart - slot)
@@ -1147,12 +1161,13 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
             if graphs is not None:
                 g = graphs.get(slot)
                 if g is None:
-                    g = graphs[slot] = IterGraph(body, [x, r, sc])
+                    g = graphs[slot] = IterGraph(body, [x, r, sc, coef])
                 g.run(mg, slot)
             else:
                 body(slot)
             slots.append(slot)
             slot = (slot + 1) % restart
+            pending = slot          # iterations whose contribution to x is still held in `coef` (flushed when the cycle wraps)
         h = sc[48:56].cpu()
         if bn2 is None:
             bn2 = float(sc[5].item())
@@ -1166,6 +1181,8 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
                 info["diverged"] = True; done = True; break
         it += nb
     info["executed_iters"] = it
+    if lazy and pending > 0:
+        call("mg2d_gcr_xupdate", _ptr(x), _ptr(Z), vs, pending, _ptr(coef), vs, dc, st())
     call("mg2d_copy", _ptr(lv0.phi), _ptr(x), vs, dc, st())
     call("mg2d_copy", _ptr(lv0.r), _ptr(b), vs, dc, st())
     info["true_resnorm"] = lv0.get_residue_mag()

@@ -168,6 +168,15 @@ int mg2d_gcr_ortho(mg2d_ctx*, void* w, void* z, const void* r, const void* W, co
                    const double* dots, const double* wn2, long long nelem, int dtype, double* out, void* stream);
 int mg2d_gcr_step(mg2d_ctx*, void* x, void* r, const void* z, const void* w, const double* wr, double* wn2_slot,
                   long long nelem, int dtype, double* out, void* stream);   /* wn2_slot (may be NULL) receives |w|^2 */
+/* Lazy solution update of the same iteration (identical iterates up to rounding): mg2d_gcr_ortho with z = Z = NULL leaves
+ * the preconditioned residuals z_i raw; mg2d_gcr_step_lazy does r -= a w, out[0] = |r|^2, *wn2_slot = |w|^2 and advances
+ * the 8 x 8 coefficient recursion in `coef` (144 doubles, device) that expresses the orthogonalised directions in the
+ * raw z_i (nj = index of this iteration within the restart cycle; nj = 0 resets); mg2d_gcr_xupdate adds the accumulated
+ * combination x += sum_{i<nj} g_i Z_i once per restart cycle (or at convergence). */
+int mg2d_gcr_step_lazy(mg2d_ctx*, void* r, const void* w, const double* wr, double* wn2_slot, const double* dots,
+                       const double* wn2, int nj, double* coef, long long nelem, int dtype, double* out, void* stream);
+int mg2d_gcr_xupdate(mg2d_ctx*, void* x, const void* Z, long long stride, int nj, const double* coef, long long nelem,
+                     int dtype, void* stream);
 int mg2d_zero(mg2d_ctx*, void* x, long long nelem, int dtype, void* stream);
 int mg2d_copy(mg2d_ctx*, void* dst, const void* src, long long nelem, int dtype, void* stream);
 /* dst = src converted between MG2D_C128 and MG2D_C64 */

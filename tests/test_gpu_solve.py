@@ -231,12 +231,22 @@ def test_gcr_outer_and_graph():
     xo, io = O.gcr_MG(LVLo, NTLo, po, b, tol=1e-10, restart=4)
     p = mg2d.make_params(L, 0.02, nlevels=2, n_smooth=2, smoother="rbgs", null_iters=40)
     mg = mg2d.setup(T(U), p)
-    for use_graph in (False, True):
-        x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=4, use_graph=use_graph, check_every=3)
-        assert ig["iters"] == io["iters"] and ig["resnorms"][io["iters"] - 1] < 1e-10      # identical outer iteration count
-        assert all(r >= 1e-10 for r in ig["resnorms"][:io["iters"] - 1])          # same first crossing
-        assert ig["true_resnorm"] < 1e-10                                        # final TRUE residual
-        assert rel(x, xo) < 1e-6
+    assert io["iters"] > 4                                                       # (the restart cycle wraps at least once)
+    xs = {}
+    for lazy in (True, False):       # raw stored directions + one solution update per restart cycle vs the textbook updates
+        mg.lazy_gcr = lazy
+        for use_graph in (False, True):
+            x, ig = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=4, use_graph=use_graph, check_every=3)
+            assert ig["iters"] == io["iters"] and ig["resnorms"][io["iters"] - 1] < 1e-10      # identical outer iteration count
+            assert all(r >= 1e-10 for r in ig["resnorms"][:io["iters"] - 1])          # same first crossing
+            assert ig["true_resnorm"] < 1e-10                                        # final TRUE residual
+            assert rel(x, xo) < 1e-6
+            x1, i1 = mg2d.solve(mg, rhs=T(b), tol=1e-10, outer="gcr", restart=4, use_graph=use_graph, check_every=1)
+            assert i1["iters"] == i1["executed_iters"] == io["iters"] and hist_close(i1["resnorms"], io["resnorms"], rtol=1e-6)
+            assert rel(x1, xo) < 1e-7 and i1["true_resnorm"] < 1e-10
+            xs[(lazy, use_graph)] = x1.clone()
+    assert float((xs[(True, True)] - xs[(False, False)]).abs().max()) < 1e-9 * float(xs[(False, False)].abs().max())
+    mg.lazy_gcr = True
     # stationary cycle from a graph equals the eager cycle
     m1 = mg2d.setup(T(U), p)
     x1, i1 = mg2d.solve(m1)
