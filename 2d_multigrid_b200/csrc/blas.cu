@@ -442,6 +442,71 @@ gcr_ortho_kernel(cplx<T>* __restrict__ w, cplx<T>* __restrict__ z, const cplx<T>
     grid_reduce<4, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
 }
 
+// The lazy variant's orthogonalisation (w only), specialised on the number of stored directions: registers (and with them
+// the resident warps) follow NJ instead of the worst case, and U independent elements per thread keep enough bytes in flight
+// when only a few streams are read (NJ = 0: w and r only).
+template <typename T, int NJ, int U>
+__global__ void __launch_bounds__(BL_THREADS)
+gcr_ortho_w_kernel(cplx<T>* __restrict__ w, const cplx<T>* __restrict__ r, const cplx<T>* __restrict__ W, long long stride,
+                   const double* __restrict__ dots, const double* __restrict__ wn2, long long n,
+                   double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
+    using C = cplx<T>;
+    __shared__ C s_beta[NJ > 0 ? NJ : 1];
+    if ((int)threadIdx.x < NJ) {
+        const double d = wn2[threadIdx.x];
+        s_beta[threadIdx.x] = d > 0.0 ? mk<T>((T)(-dots[2 * threadIdx.x] / d), (T)(-dots[2 * threadIdx.x + 1] / d)) : mk<T>(0, 0);
+    }
+    __syncthreads();
+    double red[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e0 < n; e0 += nthreads * U) {
+        C wv[U], rv[U], Wv[U][NJ > 0 ? NJ : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * nthreads;
+            if (e < n) {
+                wv[u] = w[e]; rv[u] = __ldg(r + e);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) Wv[u][j] = __ldg(W + (size_t)j * stride + e);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * nthreads;
+            if (e < n) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) cfma(wv[u], s_beta[j], Wv[u][j]);
+                w[e] = wv[u];
+                red[0] += (double)wv[u].x * wv[u].x + (double)wv[u].y * wv[u].y;
+                red[1] += (double)wv[u].x * rv[u].x + (double)wv[u].y * rv[u].y;       // <w, r> = conj(w) r
+                red[2] += (double)wv[u].x * rv[u].y - (double)wv[u].y * rv[u].x;
+            }
+        }
+    }
+    grid_reduce<4, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
+}
+
+template <typename T>
+int launch_ortho_w(mg2d_ctx* ctx, void* w, const void* r, const void* W, long long stride, int nj, const double* dots,
+                   const double* wn2, long long nelem, double* out, cudaStream_t st) {
+    using C = cplx<T>;
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
+#define OW(NJ, U) gcr_ortho_w_kernel<T, NJ, U><<<stream_grid(ctx, nelem, U), BL_THREADS, 0, st>>>((C*)w, (const C*)r, (const C*)W, stride, dots, wn2, nelem, ctx->partials, ctx->counter, out, xc)
+    switch (nj) {
+        case 0: OW(0, 4); break;
+        case 1: OW(1, 4); break;
+        case 2: OW(2, 2); break;
+        case 3: OW(3, 2); break;
+        case 4: OW(4, 2); break;
+        case 5: OW(5, 1); break;
+        case 6: OW(6, 1); break;
+        case 7: OW(7, 1); break;
+        default: OW(8, 1); break;
+    }
+#undef OW
+    return mg2d_check_launch(ctx, "mg2d_gcr_ortho");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BL_THREADS)
 gcr_step_kernel(cplx<T>* __restrict__ x, cplx<T>* __restrict__ r, const cplx<T>* __restrict__ z, const cplx<T>* __restrict__ w,
@@ -572,6 +637,11 @@ extern "C" int mg2d_gcr_ortho(mg2d_ctx* ctx, void* w, void* z, const void* r, co
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_ortho: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(ctx, nelem);
+    if (!z) {
+        if (dtype == MG2D_C128) return launch_ortho_w<double>(ctx, w, r, W, stride, nj, dots, wn2, nelem, out, st);
+        if (dtype == MG2D_C64) return launch_ortho_w<float>(ctx, w, r, W, stride, nj, dots, wn2, nelem, out, st);
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_ortho: bad dtype");
+    }
     XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
     DISPATCH_T(dtype,
         (gcr_ortho_kernel<double><<<grid, BL_THREADS, 0, st>>>((double2*)w, (double2*)z, (const double2*)r, (const double2*)W, (const double2*)Z, stride, nj, dots, wn2, nelem, ctx->partials, ctx->counter, out, xc)),

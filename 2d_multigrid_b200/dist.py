@@ -246,9 +246,14 @@ class DistMG(MG):
         super().__init__(params, device)
         self.comm = comm
         self.min_rows = min_rows
-        if params.ntl:
-            raise NotImplementedError("the non-telescoping cycle shifts aggregates across strip boundaries: one GPU only")
         self.plan = plan_strips(params, comm.world, min_rows) if plan is None else plan
+        if params.ntl and self.plan[params.nlevels - 1][0]:
+            # f_MG_ntl (S6/modules_main.h:386-439) shifts the aggregates of level nlevels-1 by one site per quadrant
+            # (f_get_base_site, S6/modules_indiv.h:6-14): on a strip they would straddle the cut.  Supported whenever that level is
+            # one of the replicated (agglomerated) ones -- then every rank runs the four copies locally, as on one GPU.
+            raise NotImplementedError(f"non-telescoping cycle: level {params.nlevels - 1} (where the shifted copies live) must be "
+                                      f"replicated, but {self.plan[params.nlevels - 1][1]} rows per rank keep it striped; "
+                                      "raise min_rows / MG2D_MIN_ROWS or use fewer ranks")
         if not self.plan[0][0]:
             raise ValueError(f"lattice {params.L} cannot be cut into {comm.world} strips of >= {min_rows} rows in whole aggregates")
         for lv, (d, rows) in zip(self.LVL, self.plan):

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,8 @@ from . import _lib
 from ._lib import Context, MG2DError
 from .params import MGParams
 from .rng import StdMT19937
+
+GCR_PAD = int(os.environ.get("MG2D_GCR_PAD", "0"))     # extra elements between stored FGCR directions (A/B knob; measured: no effect)
 
 _DT = {"complex128": (torch.complex128, _lib.C128), "complex64": (torch.complex64, _lib.C64)}
 
@@ -100,6 +103,12 @@ class Level:
         key = (name, nvec)
         if key not in self._work:
             self._work[key] = self.new_field(nvec)
+        return self._work[key]
+
+    def flat_work(self, key, nelem: int):
+        """A flat work buffer of `nelem` field elements (callers carve padded vectors out of it)."""
+        if key not in self._work:
+            self._work[key] = torch.zeros(nelem, dtype=self.mg.tdtype, device=self.mg.device)
         return self._work[key]
 
     def dots(self, name: str = "dots"):
@@ -627,6 +636,10 @@ class MG:
                 per_site = lv.nc * lv.n
                 self.ctx.call("mg2d_fill_uniform", _ptr(lv.phi_null), lv.S * per_site, lv.y0 * lv.L * per_site, seed, lv.lvl,
                               -math.pi, math.pi, self.dcode, _stream())
+        if self.p.ntl and self.p.nlevels > 0:       # the copies of f_init_NTL (S6/modules_main.h:7-37), zero instead of random starts
+            for lvl in (self.p.nlevels - 1, self.p.nlevels):
+                for q in range(self.p.n_copies):
+                    self.NTL[lvl][q].phi, self.NTL[lvl][q].r = self.NTL[lvl][q].new_field(), self.NTL[lvl][q].new_field()
 
     def set_gauge(self, U):
         """U: the full link field [L*L, 2] (each strip keeps its own rows) or already the local rows."""
@@ -720,15 +733,26 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
     p = mg.p
     quad = p.quad if quad is None else quad
     worst = []
+    marks = []          # CUDA events around the phases of every level (resolved below, after the status read has synchronised)
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
     for lvl in range(p.nlevels):
         lv = mg.LVL[lvl]
+        m = [mark()]
         if gen_null == 1:
             lv.near_null()
+        m.append(mark())
         lv.norm_nn(quad)
         lv.ortho(quad)
         lv.ortho(quad)
         worst.append(lv.check_ortho(quad))
+        m.append(mark())
         compute_coarse_matrix(mg.LVL[lvl + 1], lv, lv, quad)
+        m.append(mark())
+        marks.append(m)
     if p.ntl:
         lo = p.nlevels - 1
         for q in range(p.n_copies):
@@ -753,6 +777,10 @@ def compute_near_null(mg: MG, quad: int | None = None, gen_null: int = 1):
         raise FloatingPointError(f"near-null orthonormalisation failed (status {int(st[0])}): NaN or tiny norm "
                                  "(S6/modules_indiv.h:119-126, S6/near_null.h:149-159)")
     mg.info["ortho_worst"] = worst
+    torch.cuda.synchronize()
+    mg.info["setup_phases"] = [{"level": l, "sites": mg.LVL[l].S, "near_null_ms": m[0].elapsed_time(m[1]),
+                                "ortho_ms": m[1].elapsed_time(m[2]), "coarse_matrix_ms": m[2].elapsed_time(m[3])}
+                               for l, m in enumerate(marks)]
     if p.stencil == "wilson" and p.chiral_transfer:
         for lvl in range(p.nlevels):
             mg.LVL[lvl].compact_projector(check=(gen_null != 1))
@@ -1089,7 +1117,12 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
     call, dc, st = mg.ctx.call, mg.dcode, _stream
     x, b = lv0.work("gcr_x"), lv0.work("gcr_b")
     r = lv0.work("gcr_r")
-    Z, W = lv0.work("gcr_Z", restart), lv0.work("gcr_W", restart)
+    # stored directions `stride` elements apart (MG2D_GCR_PAD: a 4096^2 field is exactly 2^29 bytes and up to 10 such streams are
+    # read at the same offset at the same time; padding the stride was measured to make no difference on B200)
+    stride = vs + GCR_PAD
+    Zb, Wb = lv0.flat_work(("gcr_Z", restart, GCR_PAD), restart * stride), lv0.flat_work(("gcr_W", restart, GCR_PAD), restart * stride)
+    Z = [Zb[j * stride:j * stride + vs].view(lv0.S, lv0.n) for j in range(restart)]
+    W = [Wb[j * stride:j * stride + vs].view(lv0.S, lv0.n) for j in range(restart)]
     lazy = bool(mg.lazy_gcr)
     coef = lv0.dots("gcr_coef")     # lazy update: coefficients of the orthogonalised directions in the raw z_i (mg2d_gcr_step_lazy)
     sc = lv0.dots("gcr")            # [0:4] |w|^2,<w,r> ; [4] |r|^2 ; [5] |b|^2 ; [16:32] <W_j,w> ; [40+j] |w_j|^2 ; [48+j] |r|^2 after slot j
@@ -1127,20 +1160,20 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         # classical Gram-Schmidt against the stored directions, then the minimal-residual step (3 fused passes)
         if slot > 0:
             with lv0.global_sums(sc[16:16 + 2 * slot]):
-                call("mg2d_gcr_dots", _ptr(W), vs, slot, _ptr(w), vs, dc, _ptr(sc[16:]), st())
+                call("mg2d_gcr_dots", _ptr(Wb), stride, slot, _ptr(w), vs, dc, _ptr(sc[16:]), st())
         if lazy:
             # the z_i stay raw and x is updated once per restart cycle: (2j+9) instead of (3j+14) vector passes
             with lv0.global_sums(sc[0:4]):
-                call("mg2d_gcr_ortho", _ptr(w), None, _ptr(r), _ptr(W), None, vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
+                call("mg2d_gcr_ortho", _ptr(w), None, _ptr(r), _ptr(Wb), None, stride, slot, _ptr(sc[16:]), _ptr(sc[40:]),
                      vs, dc, _ptr(sc[0:]), st())
             with lv0.global_sums(sc[48 + slot:49 + slot]):
                 call("mg2d_gcr_step_lazy", _ptr(r), _ptr(w), _ptr(sc[0:]), _ptr(sc[40 + slot:]), _ptr(sc[16:]), _ptr(sc[40:]), slot,
                      _ptr(coef), vs, dc, _ptr(sc[48 + slot:]), st())
             if slot == restart - 1:
-                call("mg2d_gcr_xupdate", _ptr(x), _ptr(Z), vs, restart, _ptr(coef), vs, dc, st())
+                call("mg2d_gcr_xupdate", _ptr(x), _ptr(Zb), stride, restart, _ptr(coef), vs, dc, st())
             return
         with lv0.global_sums(sc[0:4]):
-            call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(r), _ptr(W), _ptr(Z), vs, slot, _ptr(sc[16:]), _ptr(sc[40:]),
+            call("mg2d_gcr_ortho", _ptr(w), _ptr(z), _ptr(r), _ptr(Wb), _ptr(Zb), stride, slot, _ptr(sc[16:]), _ptr(sc[40:]),
                  vs, dc, _ptr(sc[0:]), st())
         with lv0.global_sums(sc[48 + slot:49 + slot]):
             call("mg2d_gcr_step", _ptr(x), _ptr(r), _ptr(z), _ptr(w), _ptr(sc[0:]), _ptr(sc[40 + slot:]), vs, dc,
@@ -1182,7 +1215,7 @@ def gcr_MG(mg: MG, tol: float | None = None, max_iters: int | None = None, resta
         it += nb
     info["executed_iters"] = it
     if lazy and pending > 0:
-        call("mg2d_gcr_xupdate", _ptr(x), _ptr(Z), vs, pending, _ptr(coef), vs, dc, st())
+        call("mg2d_gcr_xupdate", _ptr(x), _ptr(Zb), stride, pending, _ptr(coef), vs, dc, st())
     call("mg2d_copy", _ptr(lv0.phi), _ptr(x), vs, dc, st())
     call("mg2d_copy", _ptr(lv0.r), _ptr(b), vs, dc, st())
     info["true_resnorm"] = lv0.get_residue_mag()

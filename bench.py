@@ -494,10 +494,17 @@ def main():
         t_rb1a = time_kernel(lambda: l1.relax(1, smoother="rbgs"), 10, None if big else flush)
         t_rb1b = time_kernel(lambda: l1.relax(3, smoother="rbgs"), 6, None if big else flush)
         t_rb1 = (t_rb1b - t_rb1a) / 2
-        kern.append((f"stencil_rb_pm_kernel<double,{n1},1,2> x2 (one red-black GS sweep on pre-multiplied blocks, level 1)",
-                     (4 * n1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
-        kern.append((f"stencil_rb_pm_kernel<double,{n1},1,1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
-                     (5 * n1 * n1 + 4 * n1) * 16.0 * l1.S, t_rb1a))
+        if l1.lr_rank and mg.lowrank:
+            R1 = l1.lr_rank      # rank-R factors of the 4 hopping blocks: 2 * 4R * n numbers per site instead of 4 n^2
+            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},2> x2 (one red-black GS sweep on the rank-{R1} factors of the pre-multiplied "
+                         f"hopping blocks, level 1)", (8 * R1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
+            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
+                         (8 * R1 * n1 + n1 * n1 + 4 * n1) * 16.0 * l1.S, t_rb1a))
+        else:
+            kern.append((f"stencil_rb_pm_kernel<double,{n1},1,2> x2 (one red-black GS sweep on pre-multiplied blocks, level 1)",
+                         (4 * n1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
+            kern.append((f"stencil_rb_pm_kernel<double,{n1},1,1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
+                         (5 * n1 * n1 + 4 * n1) * 16.0 * l1.S, t_rb1a))
         c, d_ = l1.new_field(), l1.new_field()
         c.normal_()
         t_ap1 = time_kernel(lambda: l1.apply_D(d_, c), 10, flush if l1.S * n1 * n1 * 80 < 2e8 else None)
@@ -527,6 +534,24 @@ def main():
                 traffic *= 2          # the timed unit is a full sweep = two half-sweep launches
         except Exception:
             traffic = None
+
+    # ---- setup on the scoreboard: wall time, device time per phase and level, and the roofline of its dominant kernel
+    # (f_near_null, S6/level.h:177-249: null_iters relaxation sweeps of all near-null candidates, batched) ----------
+    phases = mg.info.get("setup_phases", [])
+    setup_block = {"value": t_setup, "unit": "s", "null_iters": p.null_iters, "phases": phases}
+    if phases:
+        top = max(phases, key=lambda q: q["near_null_ms"])
+        lt = mg.LVL[top["level"]]
+        nv = lt.nc // 2
+        if top["level"] == 0:       # matrix-free two-colour sweep per vector: 128 B per site and sweep
+            by = 128.0 * lt.S * nv * p.null_iters
+            kname = "wilson_rb2_kernel<double> (matrix-free sweeps of the 8 near-null candidates, level 0)"
+        else:                       # batched sweep on the dense pre-multiplied blocks: 4 vectors share one stream of M
+            by = ((4 * lt.n * lt.n) * (nv // 4 if nv % 4 == 0 else nv) + 3 * lt.n * nv) * 16.0 * lt.S * p.null_iters
+            kname = f"stencil_rb_pm_kernel<double,{lt.n},4,0> x2 (batched near-null relaxation, level {top['level']})"
+        setup_block["dominant"] = {"phase": f"near_null level {top['level']}", "kernel": kname, "ms": top["near_null_ms"], "bytes": by,
+                                   "gbs": by / top["near_null_ms"] / 1e6, "frac": by / top["near_null_ms"] / 1e6 / hbm,
+                                   "note": "whole phase (sweeps + renormalisations) over the algorithmic bytes of its sweeps"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded oracle sample, scaled ----------------------------------
     cpu = None
@@ -576,6 +601,7 @@ def main():
         "mixed_precision_half": {"value": ms_half, "unit": UNIT, "iters": info_h["iters"], "final_true_residual": info_h.get("true_resnorm"),
                                  "note": "as mixed_precision, with the coarse operators of the complex64 copy stored as __half2 (fp32 arithmetic)"},
         "kernels": table,
+        "setup": setup_block,
         "cpu_baseline": cpu,
         "config2_vs_reference_binary": config2,
     }

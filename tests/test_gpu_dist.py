@@ -71,6 +71,36 @@ def test_strip_code_with_self_neighbour_equals_single_gpu(fused, use_graph):
     ref.close(); dmg.close()
 
 
+def test_ntl_cycle_on_strips_with_replicated_copy_levels():
+    """f_MG_ntl (S6/modules_main.h:386-439) on the strip code: the quadrant-shifted copies live on the two coarsest levels,
+    which the plan replicates; fine levels are strips.  Same iteration count and solution as the single-GPU NTL solve; a plan
+    that would keep the copy level striped is refused."""
+    L = 128
+    U = mg2d.gauge.quenched_links_device(L, 6.0, sweeps=20, seed=1234, device=0)
+    p = mg2d.make_params(L, -0.03, nlevels=3, block=4, n_null=8, n_smooth=2, smoother="rbgs", null_iters=40, tol=1e-10, max_iters=100,
+                         ntl=True, n_copies=4)
+    rhs = torch.zeros((L * L, 2), dtype=torch.complex128, device="cuda:0")
+    rhs[L // 2 + (L // 2) * L, 0] = 1.0
+    ref = mg2d.setup(U, p, init="device")
+    x_ref, i_ref = mg2d.solve(ref, rhs=rhs, tol=1e-10)
+    x_ref = x_ref.clone()
+    assert i_ref["converged"] and len(i_ref["ntl_weights"]) == i_ref["iters"]
+    comm = dmod.Comm.single(mg2d.Context(0), torch.device("cuda", 0))
+    dmg = dmod.setup(U, p, comm, min_rows=16)
+    assert [d for d, _ in dmg.plan] == [True, True, False, False]
+    for use_graph in (False, True):
+        x, info = mg2d.solve(dmg, rhs=rhs, tol=1e-10, use_graph=use_graph)
+        assert info["converged"] and info["iters"] == i_ref["iters"]
+        assert float((x - x_ref).abs().max() / x_ref.abs().max()) < 1e-9
+        wg, wr = np.array(info["ntl_weights"]), np.array(i_ref["ntl_weights"])
+        assert np.allclose(wg[:5], wr[:5], rtol=1e-6, atol=1e-9)         # (the min-res weights of late cycles are fixed by residuals
+        assert np.allclose(wg, wr, rtol=1e-3, atol=1e-4)                 #  of order 1e-9: their last digits follow rounding)
+    assert comm.p2p_errors() == 0
+    with pytest.raises(NotImplementedError):
+        dmod.DistMG(mg2d.make_params(L, -0.03, nlevels=2, block=4, n_null=8, smoother="rbgs", ntl=True), comm, min_rows=16)
+    ref.close(); dmg.close()
+
+
 def _worker(rank, world, port, L, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)

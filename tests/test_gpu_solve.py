@@ -311,6 +311,46 @@ def test_per_level_block_sizes():
         mg2d.make_params(L, 0.0, nlevels=2, block=[3, 2])            # must divide the lattice
 
 
+def test_error_spectrum_on_device_matches_oracle_history():
+    """SURVEY 8f N4 (NB/2_spectral_analysis_solution.ipynb cell 5): the 2D FFT of phi_k - phi* per iteration, computed on the
+    device from the solver's own recorded iterates, against numpy's FFT of the oracle's iterates of the same run; and the
+    smoothing property it is there to show: relaxation alone damps the high-frequency error faster than the low-frequency one."""
+    L = 16
+    U = O.gauge_gaussian(L, 0.3)
+    po = O.Params(L=L, num_iters=2, block=2, m=0.1, nlevels=2, null_iters=40, res_threshold=1e-12, max_iters=100)
+    LVLo, NTLo = O.build_reference_problem(po, U)
+    O.compute_near_null(LVLo, NTLo, po, 1)
+    io = O.perform_MG(LVLo, NTLo, po, record_phi=True)
+    p = mg2d.make_params(L, 0.1, nlevels=2, n_smooth=2, null_iters=40, tol=1e-12, max_iters=100)
+    mg, ig = mg2d.run_reference_flow(p, T(U), record_phi=True)
+    assert ig["iters"] == io["iters"]
+    star_g, star_o = mg.LVL[0].phi, LVLo[0].phi
+    for k in (0, 1, 3):
+        sg = mg2d.diagnostics.error_spectrum(ig["phi_hist"][k].cuda(), star_g, L)
+        eo = (io["phi_hist"][k] - star_o).reshape(L, L, 2).transpose(2, 0, 1)
+        so = np.abs(np.fft.fft2(eo))
+        assert sg.is_cuda and rel(sg, so) < 1e-8
+    # the notebooks' summary (largest low- / high-frequency error amplitude) after 6 Gauss-Seidel sweeps on D e = 0 from a random
+    # error: device relaxation + device FFT against the oracle's relaxation + numpy FFT
+    import copy
+    lv = mg.LVL[0]
+    rng = np.random.default_rng(5)
+    e0 = rng.normal(size=(L * L, 2)) + 1j * rng.normal(size=(L * L, 2))
+    e = T(e0)
+    zero = torch.zeros_like(e)
+    lv.relax(6, phi=e, r=None, smoother="gs")
+    lo1, hi1 = mg2d.diagnostics.mode_amplitudes(e, zero, L)
+    o2 = copy.deepcopy(LVLo[0])
+    o2.phi, o2.r = e0.copy(), np.zeros_like(e0)
+    o2.relax(L, 6, 1)
+    so = np.abs(np.fft.fft2(o2.phi.reshape(L, L, 2).transpose(2, 0, 1)))
+    k = np.abs(np.fft.fftfreq(L, d=1.0 / L))
+    low = (k[:, None] <= L // 4) & (k[None, :] <= L // 4)
+    assert abs(lo1 - so[:, low].max()) < 1e-9 * lo1 and abs(hi1 - so[:, ~low].max()) < 1e-9 * hi1
+    lo0, hi0 = mg2d.diagnostics.mode_amplitudes(T(e0), zero, L)
+    assert lo1 < lo0 and hi1 < hi0           # relaxation damps both bands
+
+
 def test_complex64_and_mixed_precision_solves():
     """complex64 hierarchy (true residual ~1e-6 class) and the mixed-precision solve: complex64 V-cycle inside the
     complex128 FGCR must reach the same 1e-10 TRUE residual (fp64 check) as the all-complex128 solve."""

@@ -28,21 +28,24 @@ def run(pre, post, mixed, restart=8):
     torch.cuda.synchronize(); t0 = time.time()
     x, info = mg2d.solve(mg, **kw)
     torch.cuda.synchronize(); return info, (time.time() - t0) * 1e3
-configs = [
-    ("V(0,4) all", [0] * (nl + 1), [4] * (nl + 1)),
-    ("post [4,3,8,8,8]", [0] * (nl + 1), [4, 3] + [8] * (nl - 1)),
-    ("post [4,2,8,8,8]", [0] * (nl + 1), [4, 2] + [8] * (nl - 1)),
-    ("post [6,2,8,8,8]", [0] * (nl + 1), [6, 2] + [8] * (nl - 1)),
-    ("post [4,3,6,8,16]", [0] * (nl + 1), [4, 3, 6, 8, 16][:nl + 1]),
-    ("post [3,3,8,8,8]", [0] * (nl + 1), [3, 3] + [8] * (nl - 1)),
-    ("post [6,3,8,8,8]", [0] * (nl + 1), [6, 3] + [8] * (nl - 1)),
-    ("pre [0,0,2,2,0] post [4,3,4,4,8]", [0, 0, 2, 2, 0][:nl + 1], [4, 3, 4, 4, 8][:nl + 1]),
-]
-for name, pre, post in configs:
-    out = []
-    for mixed in (False,):
-        info, ms = run(pre, post, mixed)
-        out.append(f"{'c64pc' if mixed else 'c128 '}: {info['iters']:3d} it {ms:7.1f} ms conv {info['converged']} true {info['true_resnorm']:.1e}")
-    info, ms = run(pre, post, False, restart=4)
-    out.append(f"restart4: {info['iters']:3d} it {ms:7.1f} ms")
-    print(f"{name:34s} | " + " | ".join(out), flush=True)
+def configs():
+    z = [0] * (nl + 1)
+    for post in ([4, 2, 8, 8, 8], [4, 3, 8, 8, 8], [4, 4, 8, 8, 8], [3, 3, 8, 8, 8], [3, 2, 8, 8, 8], [2, 2, 8, 8, 8], [4, 2, 6, 8, 8],
+                 [4, 3, 6, 8, 8], [4, 3, 4, 8, 8], [4, 2, 4, 8, 8], [4, 4, 4, 8, 8], [6, 3, 8, 8, 8], [4, 3, 8, 4, 8]):
+        yield f"post {post[:nl + 1]}", z, post[:nl + 1]
+
+
+for null_iters in [int(v) for v in os.environ.get("MG2D_TUNE_NULL", "100").split(",")]:
+    if null_iters != p.null_iters:
+        mg.close(); del mg
+        import gc; gc.collect(); torch.cuda.empty_cache()
+        p = bench.workload_params(mg2d, L, mcrit + 1e-3)
+        p.null_iters = null_iters
+        t0 = time.time()
+        mg = mg2d.setup(U, p, init="device")
+        torch.cuda.synchronize()
+        print(f"# null_iters {null_iters}: setup {time.time() - t0:.2f} s", flush=True)
+    for name, pre, post in configs():
+        info, ms = run(pre, post, False)
+        line = f"c128: {info['iters']:3d} it {ms:7.1f} ms conv {info['converged']} true {info['true_resnorm']:.1e}"
+        print(f"null {null_iters:4d} {name:28s} | {line}", flush=True)
