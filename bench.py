@@ -528,8 +528,12 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", f"traffic_L{L}.json")
     if os.path.exists(traffic_file):
         try:
-            tj = {k.replace(" ", ""): v for k, v in json.load(open(traffic_file)).items() if isinstance(v, (int, float))}
-            traffic = tj.get(dom["kernel"].split(" ")[0].replace(" ", ""))
+            tj = {k.replace(" ", "").replace("<unnamed>::", ""): v for k, v in json.load(open(traffic_file)).items() if isinstance(v, (int, float))}
+            want = dom["kernel"].split(" ")[0].replace(" ", "")
+            traffic = tj.get(want)
+            if traffic is None:      # ncu names carry the trailing template arguments (LINK flag ...): match on the prefix
+                hits = [v for k, v in tj.items() if k.startswith(want.rstrip(">"))]
+                traffic = hits[0] if hits else None
             if traffic is not None and " x2 " in dom["kernel"]:
                 traffic *= 2          # the timed unit is a full sweep = two half-sweep launches
         except Exception:
