@@ -682,15 +682,15 @@ constexpr int HX_THREADS = 512;
 __global__ void __launch_bounds__(HX_THREADS)
 halo_exchange_kernel(const uint4* __restrict__ first, const uint4* __restrict__ last, long long src_stride16,
                      long long row16, int nvec, uint4* __restrict__ next_lo, uint4* __restrict__ prev_hi,
-                     HaloSlot* mine, HaloSlot* prev, HaloSlot* next) {
+                     HaloSlot* mine, HaloSlot* prev, HaloSlot* next, int relaxed) {
     __shared__ unsigned long long s_epoch;
     __shared__ int s_ok, s_last;
     if (threadIdx.x == 0) {
         const unsigned long long e = mine->epoch;     // only advanced after every CTA of this launch has arrived
         s_epoch = e;
         if (blockIdx.x == 0) {
-            st_release_sys(&prev->ack_next, e);       // I am prev's "next": its rows of epoch e (my lo_buf) are consumed
-            st_release_sys(&next->ack_prev, e);
+            // I am prev's "next": its rows of epoch e (my lo_buf) are consumed (by kernels that completed before this launch)
+            publish2(&prev->ack_next, &next->ack_prev, e, relaxed);
         }
         s_ok = spin_until(&mine->ack_next, e) && spin_until(&mine->ack_prev, e);
     }
@@ -722,8 +722,7 @@ halo_exchange_kernel(const uint4* __restrict__ first, const uint4* __restrict__ 
             st_release_sys(&next->flag_lo, ~0ull);
             st_release_sys(&prev->flag_hi, ~0ull);
         } else {
-            st_release_sys(&next->flag_lo, e + 1);
-            st_release_sys(&prev->flag_hi, e + 1);
+            publish2(&next->flag_lo, &prev->flag_hi, e + 1, relaxed);
             const bool ok = spin_until(&mine->flag_lo, e + 1) && spin_until(&mine->flag_hi, e + 1);
             if (!ok || ld_acquire_sys(&mine->flag_lo) == ~0ull || ld_acquire_sys(&mine->flag_hi) == ~0ull) mine->error = 1;
         }
@@ -773,7 +772,7 @@ extern "C" int mg2d_halo_exchange(mg2d_ctx* ctx, const void* first, const void* 
         (row_bytes & 15) || (src_stride_bytes & 15))
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_halo_exchange: bad argument (rows must be multiples of 16 bytes)");
     halo_exchange_kernel<<<(nvec * (row_bytes / 16) > 4096 ? HX_CTAS : 1), HX_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)first, (const uint4*)last, src_stride_bytes / 16,
-        row_bytes / 16, nvec, (uint4*)next_lo, (uint4*)prev_hi, (HaloSlot*)slot_mine, (HaloSlot*)slot_prev, (HaloSlot*)slot_next);
+        row_bytes / 16, nvec, (uint4*)next_lo, (uint4*)prev_hi, (HaloSlot*)slot_mine, (HaloSlot*)slot_prev, (HaloSlot*)slot_next, mg2d_publish_relaxed());
     return mg2d_check_launch(ctx, "mg2d_halo_exchange");
 }
 
@@ -784,7 +783,7 @@ extern "C" int mg2d_comm_create(mg2d_ctx* ctx, int world, int rank, void* const*
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_create: bad argument (at most 8 ranks)");
     XComm h;
     memset(&h, 0, sizeof(h));
-    h.world = world; h.rank = rank;
+    h.world = world; h.rank = rank; h.relaxed = mg2d_publish_relaxed();
     for (int q = 0; q < world; ++q) {
         if (!area_ptrs[q]) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_comm_create: null mailbox pointer");
         h.area[q] = (XRedArea*)area_ptrs[q];

@@ -1,5 +1,7 @@
 // common.cuh -- shared device helpers for libmg2d_sm100.so (sm_100a only).
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -31,6 +33,7 @@ struct XComm {               // local descriptor (plain device memory) of the ra
     int world, rank;
     unsigned long long epoch;                // all-reduces completed
     unsigned long long error;
+    int relaxed;                             // flags published with relaxed stores behind the one fence (mg2d_publish_relaxed)
     XRedArea* area[MG2D_MAX_RANKS];          // area[q] = rank q's mailbox (peer-mapped; area[rank] is local)
 };
 
@@ -40,7 +43,16 @@ struct HaloLinkDev {
     HaloSlot* mine; HaloSlot* prev; HaloSlot* next;
     void* push_next_lo; void* push_prev_hi;
     int wait;
+    int relaxed;     // publish flags with relaxed system-scope stores behind ONE fence (default) instead of two release stores
 };
+
+// MG2D_PUBLISH=release restores the two st.release.sys per publication (each carries its own system-scope fence: three
+// sequential NVLink round trips at the tail of every halo-linked kernel); default: __threadfence_system() once, then relaxed stores
+inline int mg2d_publish_relaxed() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MG2D_PUBLISH"); v = (e && !strcmp(e, "release")) ? 0 : 1; }
+    return v;
+}
 
 struct mg2d_ctx {
     int device;
@@ -115,9 +127,35 @@ template <typename C> __device__ __forceinline__ C shfl_c(C v, int src, int widt
     v.x = __shfl_sync(0xffffffffu, v.x, src, width); v.y = __shfl_sync(0xffffffffu, v.y, src, width); return v;
 }
 
+// Scheduling fence for a batch of loaded values: one empty asm that "modifies" all of them, so every load of the batch must
+// have been ISSUED before the first consumer can be scheduled (the compiler otherwise sinks each load next to its FMA to
+// save registers, leaving an in-order warp with 2-5 loads in flight instead of the whole batch).  No instruction is emitted.
+__device__ __forceinline__ void keep8(double2 (&v)[8]) {
+    asm volatile("" : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x), "+d"(v[3].y),
+                      "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y), "+d"(v[7].x), "+d"(v[7].y));
+}
+__device__ __forceinline__ void keep8(float2 (&v)[8]) {
+    asm volatile("" : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x), "+f"(v[3].y),
+                      "+f"(v[4].x), "+f"(v[4].y), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[6].x), "+f"(v[6].y), "+f"(v[7].x), "+f"(v[7].y));
+}
+template <typename C, int K> __device__ __forceinline__ void keep_all(C (&v)[K]) {
+    if constexpr (K % 8 == 0) {
+#pragma unroll
+        for (int b = 0; b < K; b += 8) keep8(*reinterpret_cast<C(*)[8]>(&v[b]));
+    }
+}
+
 // ---- system-scope flag accesses (peer memory over NVLink) ---------------------------------------------
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// two flags of the same value; the caller has already executed __threadfence_system() after the data they guard
+__device__ __forceinline__ void publish2(unsigned long long* a, unsigned long long* b, unsigned long long v, int relaxed) {
+    if (relaxed) { st_relaxed_sys(a, v); st_relaxed_sys(b, v); }
+    else { st_release_sys(a, v); st_release_sys(b, v); }
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -156,7 +194,8 @@ __device__ __forceinline__ void xcomm_allreduce(XComm* xc, const double* vals, i
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < world) {
-        st_release_sys(&xc->area[threadIdx.x]->flag[par][rank], e);
+        if (xc->relaxed) st_relaxed_sys(&xc->area[threadIdx.x]->flag[par][rank], e);
+        else st_release_sys(&xc->area[threadIdx.x]->flag[par][rank], e);
         if (!spin_until(&xc->area[rank]->flag[par][threadIdx.x], e)) s_ok = 0;
     }
     __syncthreads();

@@ -238,9 +238,9 @@ stencil_rb_batch_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, cons
 // and no second dependent mat-vec phase (shorter critical path on the small, latency-bound levels).
 // CMODE 0: r = 0 (near-null relaxation); 1: first sweep of a relax call, c = D0^-1 r is computed here and stored in
 // cbuf; 2: c read from cbuf.  NV vectors per pass share one stream of the blocks (blockIdx.y = batch of NV).
-// LINK (strips): boundary rows are processed last; before the first step that touches them the CTA waits for the
-// neighbours' halo rows (flags >= local epoch), every updated boundary value is also stored into the neighbour's halo
-// buffer over NVLink, and the last CTA to finish publishes epoch + 1 (see mg2d_halo_link in include/mg2d.h).
+// LINK (strips): boundary rows are processed FIRST; before its first step on them a CTA waits for the neighbours' halo rows
+// (flags >= local epoch), every updated boundary value is also stored into the neighbour's halo buffer over NVLink, and
+// the last boundary CTA to finish publishes epoch + 1 (see mg2d_halo_link in include/mg2d.h) while the interior streams.
 template <typename T, int N, int NV, int CMODE, bool LINK>
 __global__ void __launch_bounds__(ST_THREADS)
 stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ M,
@@ -259,16 +259,21 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
     if (CMODE != 0) cbuf += v0 * vstride;
     C* push_lo = nullptr; C* push_hi = nullptr;     // neighbours' buffers: next's lo halo <- my last row, prev's hi halo <- my row 0
     __shared__ unsigned long long s_epoch;
-    bool waited = false;
+    bool waited = false;                            // this CTA works on boundary rows: it has read the epoch (and waited)
+    bool ticketed = false;                          // ... and has reported the end of its boundary work
     if (LINK) {
+        // (no epoch read here: a dependent load + barrier in front of every CTA's first loads costs ~20 % of a half sweep when
+        // each CTA lives for one step; only the CTAs that reach the boundary rows need the epoch)
         if (link.push_next_lo) { push_lo = (C*)link.push_next_lo + v0 * hstride; push_hi = (C*)link.push_prev_hi + v0 * hstride; }
-        if (threadIdx.x == 0) s_epoch = link.mine->epoch;
-        __syncthreads();
     }
     const int Lh = Lx / 2;
     const long long S2 = (long long)Lh * Ly;
     const long long nsteps = (S2 + GPB - 1) / GPB;
-    const long long first_boundary = (Ly >= 2) ? (long long)(Ly - 2) * Lh : 0;      // in the remapped row order
+    // strips: the two boundary rows come FIRST (row order 0, Ly-1, 1, 2, .., Ly-2): their CTAs wait for the neighbours' rows of
+    // the previous launch (published early in that launch for the same reason), push what they produce and publish the new
+    // epoch while the interior of this launch is still streaming -- neither the fence + flag round trips at the end of the
+    // boundary work nor the neighbours' wait sit on the critical path
+    const long long nb_half = (long long)(Ly >= 2 ? 2 : 1) * Lh;                     // half-row sites of the boundary rows
     for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
         long long h = step * GPB + grp;
         const bool active = h < S2;
@@ -276,10 +281,14 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
         int y = (int)(h / Lh);
         const int xh = (int)(h - (long long)y * Lh);
         if (LINK) {
-            y = (y + 1 == Ly) ? 0 : y + 1;                                         // rows 1 .. Ly-1, then 0
-            if (link.wait && !waited && step * GPB + GPB - 1 >= first_boundary) {   // CTA-uniform
-                if (threadIdx.x == 0 && !(spin_until(&link.mine->flag_lo, s_epoch) && spin_until(&link.mine->flag_hi, s_epoch)))
-                    atomicExch(&link.mine->error, 1ull);
+            y = (y == 0) ? 0 : (y == 1 ? Ly - 1 : y - 1);                          // rows 0, Ly-1, then 1 .. Ly-2
+            if (!waited && step * GPB < nb_half) {                                   // CTA-uniform: first boundary step
+                if (threadIdx.x == 0) {
+                    const unsigned long long e = link.mine->epoch;      // advanced only after every boundary CTA has taken its ticket
+                    s_epoch = e;
+                    if ((link.wait & 1) && !(spin_until(&link.mine->flag_lo, e) && spin_until(&link.mine->flag_hi, e)))
+                        atomicExch(&link.mine->error, 1ull);
+                }
                 __syncthreads();
                 waited = true;
             }
@@ -290,18 +299,36 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
         C acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = mk<T>(0, 0);
+        // The loads are issued in explicit batches of CH block elements + their field values before any of them is consumed:
+        // left to itself the compiler interleaves load / FMA pairs to save registers, and an in-order warp then has only 2-5
+        // loads in flight (ncu, round 2: the sweep then depends on occupancy and loses 20-40 % on small strips).
+        // (halo rows are peer-written: ld.cg reads them from L2, the coherence point of NVLink-incoming stores; no
+        // inline-asm loads here -- their compiler barrier would serialise the independent loads)
+        constexpr int CH = (ITERS < 8 / NV) ? ITERS : ((8 / NV) < 2 ? 2 : 8 / NV);
+        static_assert(ITERS % CH == 0, "chunking");
 #pragma unroll
-        for (int t = 0; t < ITERS; ++t) {
-            const int k = 1 + (JP * t) / N;
-            const int j = jp + (JP * t) % N;
-            const C d = __ldg(Ms + g + G * t);
-            const bool in_hi = (k == 3 && y + 1 == Ly), in_lo = (k == 4 && y == 0);
-            const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
-            const long long st = (in_hi || in_lo) ? hstride : vstride;
+        for (int t0 = 0; t0 < ITERS; t0 += CH) {
+            C d[CH], pv[CH][NV];
 #pragma unroll
-            // (halo rows are peer-written: ld.cg reads them from L2, the coherence point of NVLink-incoming stores; no
-            // inline-asm loads here -- their compiler barrier would serialise the 32 independent loads of this loop)
-            for (int v = 0; v < NV; ++v) cfma(acc[v], d, __ldcg(p + (size_t)v * st));
+            for (int u = 0; u < CH; ++u) {
+                const int t = t0 + u;
+                const int k = 1 + (JP * t) / N;
+                const int j = jp + (JP * t) % N;
+                d[u] = __ldg(Ms + g + G * t);
+                const bool in_hi = (k == 3 && y + 1 == Ly), in_lo = (k == 4 && y == 0);
+                const C* p = nbr_ptr<C>(phi, lo, hi, k, x, y, Lx, Ly, N) + j;
+                const long long st = (in_hi || in_lo) ? hstride : vstride;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) pv[u][v] = __ldcg(p + (size_t)v * st);
+            }
+            if constexpr (NV == 1 && CH == 8) {
+                C (&pf)[CH] = *reinterpret_cast<C(*)[CH]>(&pv[0][0]);
+                keep_all(d); keep_all(pf);
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) cfma(acc[v], d[u], pv[u][v]);
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -323,18 +350,22 @@ stencil_rb_pm_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
                 }
             }
         }
-    }
-    if (LINK && push_lo) {
-        if (waited || !link.wait) __threadfence_system();      // only CTAs that did boundary work have peer stores in flight
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
-            if (t == (unsigned long long)gridDim.x * gridDim.y - 1ull) {
-                __threadfence_system();
-                link.mine->ticket = 0ull;
-                st_release_sys(&link.next->flag_lo, s_epoch + 1ull);
-                st_release_sys(&link.prev->flag_hi, s_epoch + 1ull);
-                link.mine->epoch = s_epoch + 1ull;
+        if (LINK && push_lo && waited && !ticketed && (step + gridDim.x) * GPB >= nb_half) {
+            // this CTA's last boundary step is done: only the CTAs that worked on boundary rows have peer stores in flight and
+            // only they are counted (the neighbours read nothing else of this launch); the last of them publishes
+            ticketed = true;
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const long long nbs = (nb_half + GPB - 1) / GPB;             // steps that touch the boundary rows
+                const unsigned long long nbound = (unsigned long long)(nbs < (long long)gridDim.x ? nbs : (long long)gridDim.x) * gridDim.y;
+                const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
+                if (t == nbound - 1ull) {
+                    __threadfence_system();
+                    link.mine->ticket = 0ull;
+                    publish2(&link.next->flag_lo, &link.prev->flag_hi, s_epoch + 1ull, link.relaxed);
+                    link.mine->epoch = s_epoch + 1ull;
+                }
             }
         }
     }
@@ -371,12 +402,22 @@ stencil_rb_pm_sweeps_kernel(cplx<T>* phi, const cplx<T>* __restrict__ M, const c
                 const size_t s = (size_t)y * L + x;
                 const C* Ms = M + s * 4 * N * N;
                 C acc = mk<T>(0, 0);
+                // latency-bound (a few CTAs, L2-resident operator): every load of a batch is in flight before the first FMA
+                constexpr int CH = ITERS < 16 ? ITERS : 16;
 #pragma unroll
-                for (int t = 0; t < ITERS; ++t) {
-                    const int k = 1 + (JP * t) / N;
-                    const int j = jp + (JP * t) % N;
-                    const C d = __ldg(Ms + g + G * t);
-                    cfma(acc, d, __ldcg(nbr_ptr<C>(phi, lo, phi, k, x, y, L, L, N) + j));
+                for (int t0 = 0; t0 < ITERS; t0 += CH) {
+                    C d[CH], pv[CH];
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        const int t = t0 + u;
+                        const int k = 1 + (JP * t) / N;
+                        const int j = jp + (JP * t) % N;
+                        d[u] = __ldg(Ms + g + G * t);
+                        pv[u] = __ldcg(nbr_ptr<C>(phi, lo, phi, k, x, y, L, L, N) + j);
+                    }
+                    keep_all(d); keep_all(pv);
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) cfma(acc, d[u], pv[u]);
                 }
 #pragma unroll
                 for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
@@ -428,16 +469,19 @@ stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
     const int q1 = g / LR::LP, k1 = 1 + q1 / R, j0 = (g % LR::LP) * IT;
     C* push_lo = nullptr; C* push_hi = nullptr;
     __shared__ unsigned long long s_epoch;
-    bool waited = false;
+    bool waited = false;                            // this CTA works on boundary rows (see stencil_rb_pm_kernel)
+    bool ticketed = false;
     if (LINK) {
         if (link.push_next_lo) { push_lo = (C*)link.push_next_lo; push_hi = (C*)link.push_prev_hi; }
-        if (threadIdx.x == 0) s_epoch = link.mine->epoch;
-        __syncthreads();
     }
     const int Lh = Lx / 2;
     const long long S2 = (long long)Lh * Ly;
     const long long nsteps = (S2 + GPB - 1) / GPB;
-    const long long first_boundary = (Ly >= 2) ? (long long)(Ly - 2) * Lh : 0;      // in the remapped row order
+    // strips: the two boundary rows come FIRST (row order 0, Ly-1, 1, 2, .., Ly-2): their CTAs wait for the neighbours' rows of
+    // the previous launch (published early in that launch for the same reason), push what they produce and publish the new
+    // epoch while the interior of this launch is still streaming -- neither the fence + flag round trips at the end of the
+    // boundary work nor the neighbours' wait sit on the critical path
+    const long long nb_half = (long long)(Ly >= 2 ? 2 : 1) * Lh;                     // half-row sites of the boundary rows
     for (long long step = blockIdx.x; step < nsteps; step += gridDim.x) {
         long long h = step * GPB + grp;
         const bool active = h < S2;
@@ -445,10 +489,14 @@ stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
         int y = (int)(h / Lh);
         const int xh = (int)(h - (long long)y * Lh);
         if (LINK) {
-            y = (y + 1 == Ly) ? 0 : y + 1;                                         // rows 1 .. Ly-1, then 0
-            if (link.wait && !waited && step * GPB + GPB - 1 >= first_boundary) {   // CTA-uniform
-                if (threadIdx.x == 0 && !(spin_until(&link.mine->flag_lo, s_epoch) && spin_until(&link.mine->flag_hi, s_epoch)))
-                    atomicExch(&link.mine->error, 1ull);
+            y = (y == 0) ? 0 : (y == 1 ? Ly - 1 : y - 1);                          // rows 0, Ly-1, then 1 .. Ly-2
+            if (!waited && step * GPB < nb_half) {                                   // CTA-uniform: first boundary step
+                if (threadIdx.x == 0) {
+                    const unsigned long long e = link.mine->epoch;      // advanced only after every boundary CTA has taken its ticket
+                    s_epoch = e;
+                    if (link.wait && !(spin_until(&link.mine->flag_lo, e) && spin_until(&link.mine->flag_hi, e)))
+                        atomicExch(&link.mine->error, 1ull);
+                }
                 __syncthreads();
                 waited = true;
             }
@@ -490,18 +538,20 @@ stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
                 if (y + 1 == Ly) push_lo[(size_t)x * N + i] = acc;
             }
         }
-    }
-    if (LINK && push_lo) {
-        if (waited || !link.wait) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
-            if (t == (unsigned long long)gridDim.x * gridDim.y - 1ull) {
-                __threadfence_system();
-                link.mine->ticket = 0ull;
-                st_release_sys(&link.next->flag_lo, s_epoch + 1ull);
-                st_release_sys(&link.prev->flag_hi, s_epoch + 1ull);
-                link.mine->epoch = s_epoch + 1ull;
+        if (LINK && push_lo && waited && !ticketed && (step + gridDim.x) * GPB >= nb_half) {       // (see stencil_rb_pm_kernel)
+            ticketed = true;
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const long long nbs = (nb_half + GPB - 1) / GPB;
+                const unsigned long long nbound = (unsigned long long)(nbs < (long long)gridDim.x ? nbs : (long long)gridDim.x);
+                const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
+                if (t == nbound - 1ull) {
+                    __threadfence_system();
+                    link.mine->ticket = 0ull;
+                    publish2(&link.next->flag_lo, &link.prev->flag_hi, s_epoch + 1ull, link.relaxed);
+                    link.mine->epoch = s_epoch + 1ull;
+                }
             }
         }
     }
@@ -900,7 +950,7 @@ inline HaloLinkDev make_link(const mg2d_halo_link* l) {
     memset(&d, 0, sizeof(d));
     if (l) {
         d.mine = (HaloSlot*)l->slot_mine; d.prev = (HaloSlot*)l->slot_prev; d.next = (HaloSlot*)l->slot_next;
-        d.push_next_lo = l->push_next_lo; d.push_prev_hi = l->push_prev_hi; d.wait = l->wait;
+        d.push_next_lo = l->push_next_lo; d.push_prev_hi = l->push_prev_hi; d.wait = l->wait; d.relaxed = mg2d_publish_relaxed();
     }
     return d;
 }
@@ -916,7 +966,14 @@ int launch_rb_pm(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const
     long long cap = (long long)ctx->num_sms * 32;
     const int gx = (int)(nsteps < cap ? nsteps : cap);
     const HaloLinkDev ld = make_link(link);
-#define PM(NV, CM, LK) stencil_rb_pm_kernel<T, N, NV, CM, LK><<<dim3(gx, nvec / NV), ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
+    // resident CTAs per SM are capped through (unused) dynamic shared memory: measured on B200 (ncu, 16-dof blocks), the sweep
+    // is FASTER with 5 CTAs of 256 threads per SM than with the 6 the register count would allow (90 vs 99 us for 0.56 GB):
+    // more concurrent 512-byte streams per SM only thrash DRAM pages
+    static int pm_ctas = -1;
+    if (pm_ctas < 0) { const char* e = getenv("MG2D_PM_CTAS"); pm_ctas = e ? atoi(e) : 5; if (pm_ctas < 1 || pm_ctas > 8) pm_ctas = 5; }
+    const size_t dsm = (N >= 8) ? (size_t)(200 * 1024 / pm_ctas / 1024) * 1024 - 2048 : 0;     // <= 48 KB for >= 5 CTAs (no attribute needed)
+#define PM(NV, CM, LK) (dsm > 48 * 1024 ? (void)cudaFuncSetAttribute(stencil_rb_pm_kernel<T, N, NV, CM, LK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm) : (void)0), \
+    stencil_rb_pm_kernel<T, N, NV, CM, LK><<<dim3(gx, nvec / NV), ST_THREADS, dsm, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
         (const C*)M, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, vstride, hstride, ld)
 #define PMC(NV, LK) do { if (cmode == 0) PM(NV, 0, LK); else if (cmode == 1) PM(NV, 1, LK); else PM(NV, 2, LK); } while (0)
     if (N >= 4 && nvec % 4 == 0) { if (link) PMC(4, true); else PMC(4, false); }

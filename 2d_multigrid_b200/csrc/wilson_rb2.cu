@@ -109,21 +109,26 @@ wilson_rb2_kernel(Rb2Args<T> a) {
     const int nchunks = (Ly + RY - 1) / RY;
     const long long nitems = (long long)ntx * nchunks;
     const long long wstride = (long long)gridDim.x * (RB2_THREADS / 32);
-    // strips: chunks that touch the halo rows come last (order 1, 2, .., nchunks-1, 0), wait for the neighbours' rows
-    // (flags >= local epoch) before their first halo read and store the boundary rows they produce into the
-    // neighbours' two-row halo buffers; the last CTA to finish publishes epoch + 1 (mg2d_halo_link, include/mg2d.h)
+    // strips: chunks that touch the halo rows wait for the neighbours' rows (flags >= local epoch) before their first halo
+    // read and store the boundary rows they produce into the neighbours' two-row halo buffers (mg2d_halo_link, include/mg2d.h)
     constexpr bool linked = LINKED;
     unsigned long long epoch = 0ull;
-    bool waited = false;
+    bool waited = false, ticketed = false;
     C* push_lo = nullptr; C* push_hi = nullptr;
+    // chunks whose rows touch the halo (chunk 0 and the last one or two: y1 + 2 > Ly) come FIRST, in item order
+    // 0, nchunks-1, (nchunks-2), then the interior ascending; the warps that own them report as soon as their last boundary
+    // item is stored, and the last of them publishes while the interior of this launch is still streaming
+    int ntail = 0;
     if (linked) {
-        epoch = a.link.mine->epoch;
         push_lo = (C*)a.link.push_next_lo; push_hi = (C*)a.link.push_prev_hi;
+        if (nchunks >= 2) ntail = 1;
+        if (nchunks >= 3 && (long long)(nchunks - 1) * RY + 2 > Ly) ntail = 2;
     }
+    const long long nbi = (long long)ntx * (1 + ntail);         // boundary items (they are the first nbi items)
     for (long long item = (long long)blockIdx.x * (RB2_THREADS / 32) + (threadIdx.x >> 5); item < nitems; item += wstride) {
         int chunk = (int)(item / ntx);
         const int tile = (int)(item - (long long)chunk * ntx);
-        if (linked) chunk = (chunk + 1 == nchunks) ? 0 : chunk + 1;
+        if (linked) chunk = (chunk == 0) ? 0 : (chunk <= ntail ? nchunks - chunk : chunk - ntail);
         const int X0 = tile * RB2_W;
         const int y0 = chunk * RY, y1 = min(y0 + RY, Ly);
         // the lane's two columns: c0 = X0 + 2*lane - 1 (odd), c1 = X0 + 2*lane (even), periodic
@@ -135,8 +140,10 @@ wilson_rb2_kernel(Rb2Args<T> a) {
         const int xm_out = (x0 == 0) ? Lx - 1 : x0 - 1;            // lane 0: column left of the tile
         const int xp_out = (x1 + 1 == Lx) ? 0 : x1 + 1;            // lane 31: column right of the tile
 
-        if (linked && a.link.wait && !waited && (y0 < 2 || y1 + 2 > Ly)) {           // warp-uniform
-            if (lane == 0 && !(spin_until(&a.link.mine->flag_lo, epoch) && spin_until(&a.link.mine->flag_hi, epoch)))
+        if (linked && !waited && item < nbi) {                                        // warp-uniform: first boundary item
+            // (the epoch only advances after every boundary warp has taken its ticket, i.e. after this read)
+            epoch = a.link.mine->epoch;
+            if (a.link.wait && lane == 0 && !(spin_until(&a.link.mine->flag_lo, epoch) && spin_until(&a.link.mine->flag_hi, epoch)))
                 atomicExch(&a.link.mine->error, 1ull);
             __syncwarp();
             waited = true;
@@ -205,18 +212,20 @@ wilson_rb2_kernel(Rb2Args<T> a) {
             umm_uy0 = um_uy0; umm_uy1 = um_uy1;
             um_ux0 = u0_ux0; um_uy0 = u0_uy0; um_ux1 = u0_ux1; um_uy1 = u0_uy1;
         }
-    }
-    if (linked && push_lo) {
-        if (waited || !a.link.wait) __threadfence_system();    // only warps that did boundary work have peer stores in flight
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long t = atomicAdd(&a.link.mine->ticket, 1ull);
-            if (t == (unsigned long long)gridDim.x - 1ull) {
-                __threadfence_system();
-                a.link.mine->ticket = 0ull;
-                st_release_sys(&a.link.next->flag_lo, epoch + 1ull);
-                st_release_sys(&a.link.prev->flag_hi, epoch + 1ull);
-                a.link.mine->epoch = epoch + 1ull;
+        if (linked && push_lo && waited && !ticketed && item + wstride >= nbi) {
+            // this warp's last boundary item is stored (only boundary warps have peer stores in flight, only they are counted)
+            ticketed = true;
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned long long nbw = (unsigned long long)(nbi < wstride ? nbi : wstride);     // warps that own boundary items
+                const unsigned long long t = atomicAdd(&a.link.mine->ticket, 1ull);
+                if (t == nbw - 1ull) {
+                    __threadfence_system();
+                    a.link.mine->ticket = 0ull;
+                    publish2(&a.link.next->flag_lo, &a.link.prev->flag_hi, epoch + 1ull, a.link.relaxed);
+                    a.link.mine->epoch = epoch + 1ull;
+                }
             }
         }
     }
@@ -231,7 +240,7 @@ int launch_rb2(mg2d_ctx* ctx, void* out, const void* in, const void* in_lo2, con
     memset(&a.link, 0, sizeof(a.link));
     if (link) {
         a.link.mine = (HaloSlot*)link->slot_mine; a.link.prev = (HaloSlot*)link->slot_prev; a.link.next = (HaloSlot*)link->slot_next;
-        a.link.push_next_lo = link->push_next_lo; a.link.push_prev_hi = link->push_prev_hi; a.link.wait = link->wait;
+        a.link.push_next_lo = link->push_next_lo; a.link.push_prev_hi = link->push_prev_hi; a.link.wait = link->wait; a.link.relaxed = mg2d_publish_relaxed();
     }
     a.out = (C*)out; a.in = (const C*)in; a.in_lo2 = (const C*)in_lo2; a.in_hi2 = (const C*)in_hi2;
     a.U = (const C*)U; a.U_lo2 = (const C*)U_lo2; a.U_hi = (const C*)U_hi;

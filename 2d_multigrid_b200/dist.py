@@ -34,6 +34,7 @@ MIN_ROWS = int(os.environ.get("MG2D_MIN_ROWS", "32"))
 HALO_MODE = os.environ.get("MG2D_HALO", "p2p")      # 'p2p': NVLink peer stores from our own kernels; 'nccl': send/recv
 FUSED = os.environ.get("MG2D_FUSED", "1") != "0"    # p2p only: halo push fused into the smoother kernels, reductions
                                                     # summed over ranks inside the producing kernel
+LINK_DEBUG = os.environ.get("MG2D_LINK_DEBUG", "")   # 'nowait' / 'nopush': tools/ablate.py timing experiments (wrong results)
 SLAB_BYTES = int(os.environ.get("MG2D_P2P_SLAB_MB", "256")) << 20
 SLOT_REGION = 1 << 16                                # 1024 halo slots of 64 bytes at the start of the slab
 MAILBOX_OFF = 1 << 16                                # all-reduce mailbox (XRedArea) of the rank
@@ -157,8 +158,11 @@ class Comm:
         b = st["base"]
         me, pv, nx = b[self.rank], b[self.prev], b[self.next]
         rd, wr = phase & 1, (phase + 1) & 1
+        if LINK_DEBUG == "nopush":      # timing experiments only (results are wrong): kernels neither push nor wait
+            push = False
         link = HaloLink(me + e["slot"], pv + e["slot"], nx + e["slot"],
-                        (nx + e["lo"][wr]) if push else None, (pv + e["hi"][wr]) if push else None, 1)
+                        (nx + e["lo"][wr]) if push else None, (pv + e["hi"][wr]) if push else None,
+                        {"nowait": 0, "nopush": 0}.get(LINK_DEBUG, 1))
         return link, me + e["lo"][rd], me + e["hi"][rd]
 
     def check_errors(self):
