@@ -455,24 +455,29 @@ template <int N, int R> struct LowRank {
     static_assert(Q <= 32 && (32 % Q) == 0 && (32 % N) == 0 && N >= 8 && (N * R) % 8 == 0 && LP * IT == N, "unsupported (N, R)");
 };
 
-template <typename T, int N, int R, int CMODE, bool LINK>
+// NV vectors per pass share one stream of the factors (blockIdx.y = batch of NV; near-null generation).
+template <typename T, int N, int R, int NV, int CMODE, bool LINK>
 __global__ void __launch_bounds__(ST_THREADS)
 stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ F,
                      const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, cplx<T>* cbuf, int Lx, int Ly,
-                     int colour, int yoff, HaloLinkDev link) {
+                     int colour, int yoff, long long vstride, long long hstride, HaloLinkDev link) {
     using C = cplx<T>;
     using LR = LowRank<N, R>;
     constexpr int G = 32, GPB = ST_THREADS / G, IT = LR::IT;
-    __shared__ C s_t[GPB][LR::Q];
+    __shared__ C s_t[GPB][NV][LR::Q];
     const int g = threadIdx.x % G, grp = threadIdx.x / G;
     const int i = g % N;
     const int q1 = g / LR::LP, k1 = 1 + q1 / R, j0 = (g % LR::LP) * IT;
+    const size_t v0 = (size_t)blockIdx.y * NV;
+    phi += v0 * vstride; lo += v0 * hstride; hi += v0 * hstride;
+    if (CMODE == 1) r += v0 * vstride;
+    if (CMODE != 0) cbuf += v0 * vstride;
     C* push_lo = nullptr; C* push_hi = nullptr;
     __shared__ unsigned long long s_epoch;
     bool waited = false;                            // this CTA works on boundary rows (see stencil_rb_pm_kernel)
     bool ticketed = false;
     if (LINK) {
-        if (link.push_next_lo) { push_lo = (C*)link.push_next_lo; push_hi = (C*)link.push_prev_hi; }
+        if (link.push_next_lo) { push_lo = (C*)link.push_next_lo + v0 * hstride; push_hi = (C*)link.push_prev_hi + v0 * hstride; }
     }
     const int Lh = Lx / 2;
     const long long S2 = (long long)Lh * Ly;
@@ -510,41 +515,49 @@ stencil_rb_lr_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const c
 #pragma unroll
         for (int t = 0; t < IT; ++t) ma[t] = __ldg(Fs + 32 * IT + 32 * t + g);
         const C* pn = nbr_ptr<C>(phi, lo, hi, k1, x, y, Lx, Ly, N) + j0;
-        C tq = mk<T>(0, 0);
+        const bool halo_row = (k1 == 3 && y + 1 == Ly) || (k1 == 4 && y == 0);
+        const long long st = halo_row ? hstride : vstride;
 #pragma unroll
-        for (int t = 0; t < IT; ++t) cfma(tq, bc[t], __ldcg(pn + t));
+        for (int v = 0; v < NV; ++v) {
+            C tq = mk<T>(0, 0);
 #pragma unroll
-        for (int m = 1; m < LR::LP; m <<= 1) tq = cadd(tq, shfl_xor_c(tq, m));
-        if ((g % LR::LP) == 0) s_t[grp][q1] = tq;
-        __syncwarp();
-        C acc = mk<T>(0, 0);
+            for (int t = 0; t < IT; ++t) cfma(tq, bc[t], __ldcg(pn + (size_t)v * st + t));
 #pragma unroll
-        for (int t = 0; t < IT; ++t) cfma(acc, ma[t], s_t[grp][t * LR::H + g / N]);
-#pragma unroll
-        for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
-        __syncwarp();
-        if (CMODE == 1) {
-            const C w = __ldg(r + s * N + i);
-            const C c = apply_minus_inv<T, N, G>(Dinv + s * N * N, w, g);       // = -D0^-1 r
-            acc = csub(acc, c);
-            if (active && g < N) cbuf[s * N + i] = mk<T>(-c.x, -c.y);
-        } else if (CMODE == 2) {
-            acc = cadd(acc, __ldg(cbuf + s * N + i));
+            for (int m = 1; m < LR::LP; m <<= 1) tq = cadd(tq, shfl_xor_c(tq, m));
+            if ((g % LR::LP) == 0) s_t[grp][v][q1] = tq;
         }
-        if (active && g < N) {
-            phi[s * N + i] = acc;
-            if (LINK && push_lo) {
-                if (y == 0) push_hi[(size_t)x * N + i] = acc;
-                if (y + 1 == Ly) push_lo[(size_t)x * N + i] = acc;
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            C acc = mk<T>(0, 0);
+#pragma unroll
+            for (int t = 0; t < IT; ++t) cfma(acc, ma[t], s_t[grp][v][t * LR::H + g / N]);
+#pragma unroll
+            for (int m = N; m < G; m <<= 1) acc = cadd(acc, shfl_xor_c(acc, m));
+            if (CMODE == 1) {
+                const C w = __ldg(r + (size_t)v * vstride + s * N + i);
+                const C c = apply_minus_inv<T, N, G>(Dinv + s * N * N, w, g);       // = -D0^-1 r
+                acc = csub(acc, c);
+                if (active && g < N) cbuf[(size_t)v * vstride + s * N + i] = mk<T>(-c.x, -c.y);
+            } else if (CMODE == 2) {
+                acc = cadd(acc, __ldg(cbuf + (size_t)v * vstride + s * N + i));
+            }
+            if (active && g < N) {
+                phi[(size_t)v * vstride + s * N + i] = acc;
+                if (LINK && push_lo) {
+                    if (y == 0) push_hi[(size_t)v * hstride + (size_t)x * N + i] = acc;
+                    if (y + 1 == Ly) push_lo[(size_t)v * hstride + (size_t)x * N + i] = acc;
+                }
             }
         }
+        __syncwarp();
         if (LINK && push_lo && waited && !ticketed && (step + gridDim.x) * GPB >= nb_half) {       // (see stencil_rb_pm_kernel)
             ticketed = true;
             __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {
                 const long long nbs = (nb_half + GPB - 1) / GPB;
-                const unsigned long long nbound = (unsigned long long)(nbs < (long long)gridDim.x ? nbs : (long long)gridDim.x);
+                const unsigned long long nbound = (unsigned long long)(nbs < (long long)gridDim.x ? nbs : (long long)gridDim.x) * gridDim.y;
                 const unsigned long long t = atomicAdd(&link.mine->ticket, 1ull);
                 if (t == nbound - 1ull) {
                     __threadfence_system();
@@ -1033,7 +1046,8 @@ int dispatch_rb_pm_sweeps(mg2d_ctx* ctx, int n, void* phi, const void* M, const 
 
 template <typename T, int N, int R>
 int launch_rb_lr(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* F, const void* Dinv, const void* r,
-                 void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, const mg2d_halo_link* link, cudaStream_t st) {
+                 void* cbuf, int cmode, int Lx, int Ly, int colour, int yoff, int nvec, long long vstride, long long hstride,
+                 const mg2d_halo_link* link, cudaStream_t st) {
     using C = cplx<T>;
     constexpr int GPB = ST_THREADS / 32;
     const long long S2 = (long long)(Lx / 2) * Ly;
@@ -1041,10 +1055,11 @@ int launch_rb_lr(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const
     long long cap = (long long)ctx->num_sms * 32;
     const int gx = (int)(nsteps < cap ? nsteps : cap);
     const HaloLinkDev ld = make_link(link);
-#define LRK(CM, LK) stencil_rb_lr_kernel<T, N, R, CM, LK><<<gx, ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
-        (const C*)F, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, ld)
-#define LRC(LK) do { if (cmode == 0) LRK(0, LK); else if (cmode == 1) LRK(1, LK); else LRK(2, LK); } while (0)
-    if (link) LRC(true); else LRC(false);
+#define LRK(NV, CM, LK) stencil_rb_lr_kernel<T, N, R, NV, CM, LK><<<dim3(gx, nvec / NV), ST_THREADS, 0, st>>>((C*)phi, (const C*)lo, (const C*)hi, \
+        (const C*)F, (const C*)Dinv, (const C*)r, (C*)cbuf, Lx, Ly, colour, yoff, vstride, hstride, ld)
+#define LRC(NV, LK) do { if (cmode == 0) LRK(NV, 0, LK); else if (cmode == 1) LRK(NV, 1, LK); else LRK(NV, 2, LK); } while (0)
+    if (nvec % 4 == 0) { if (link) LRC(4, true); else LRC(4, false); }
+    else               { if (link) LRC(1, true); else LRC(1, false); }
 #undef LRC
 #undef LRK
     return mg2d_check_launch(ctx, "mg2d_relax_rb_lr");
@@ -1218,14 +1233,15 @@ extern "C" int mg2d_lowrank_supported(int n, int rank) {
 
 extern "C" int mg2d_relax_rb_lr(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* F, const void* D0inv,
                                 const void* r, void* cbuf, int cmode, int n, int rank, int Lx, int Ly, int colour, int yoff,
-                                int dtype, const struct mg2d_halo_link* link, void* stream) {
+                                int dtype, int nvec, long long vstride, long long hstride, const struct mg2d_halo_link* link,
+                                void* stream) {
     if (!ctx) return MG2D_EINVAL;
     if (!phi || !phi_lo || !phi_hi || !F || Lx < 2 || (Lx & 1) || Ly < 1 || cmode < 0 || cmode > 2 || (cmode == 1 && (!r || !D0inv)) ||
-        (cmode != 0 && !cbuf))
+        (cmode != 0 && !cbuf) || nvec < 1)
         return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_lr: bad argument (Lx must be even)");
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL_D(N, R) return launch_rb_lr<double, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, link, st)
-#define CALL_F(N, R) return launch_rb_lr<float, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, link, st)
+#define CALL_D(N, R) return launch_rb_lr<double, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st)
+#define CALL_F(N, R) return launch_rb_lr<float, N, R>(ctx, phi, phi_lo, phi_hi, F, D0inv, r, cbuf, cmode, Lx, Ly, colour, yoff, nvec, vstride, hstride, link, st)
     if (dtype == MG2D_C128) { MG2D_LR_CASES(CALL_D) }
     else if (dtype == MG2D_C64) { MG2D_LR_CASES(CALL_F) }
     else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_rb_lr: bad dtype");

@@ -370,22 +370,23 @@ class Level:
                             lo, hi = self._halo(ph)
                             mg.ctx.call("mg2d_wilson_relax_rb", _ptr(ph), lo, hi, _ptr(self.U), self.U_lo_ptr, _ptr(rv),
                                         float(mg.p.mass), self.L, self.Ly, colour, self.y0 & 1, mg.dcode, _stream())
-                    elif self.lr_rank and nvec == 1 and mg.premul and mg.lowrank and self._ensure_F():
-                        # first coarse level: rank-`block` factors of the pre-multiplied hopping blocks (half the bytes)
+                    elif self.lr_rank and mg.premul and mg.lowrank and self._ensure_F():
+                        # first coarse level: rank-`block` factors of the pre-multiplied hopping blocks (half the bytes);
+                        # batches of 4 vectors share one stream of the factors (near-null generation)
                         cmode = 0 if r is None else (1 if it == 0 else 2)
-                        cbuf = None if r is None else self.work("pm_c")
+                        cbuf = None if r is None else self.work("pm_c", None if nvec == 1 else nvec)
                         link = None
                         if self.distributed and mg.comm.fused:
                             k = 2 * it + colour
                             if k == 0:
-                                self._halo(phi)
-                            lk, lo, hi = mg.comm.fused_link(phi, self.L, self.Ly, self.n, 1, (self.lvl, self.n, 1, 1), 1, k,
+                                self._halo(phi, nvec)
+                            lk, lo, hi = mg.comm.fused_link(phi, self.L, self.Ly, self.n, nvec, (self.lvl, self.n, nvec, 1), 1, k,
                                                             push=(k < 2 * num_iter - 1))
                             link = ctypes.byref(lk)
                         else:
-                            lo, hi = self._halo(phi)
+                            lo, hi = self._halo(phi, nvec)
                         mg.ctx.call("mg2d_relax_rb_lr", _ptr(phi), lo, hi, _ptr(self.F), _ptr(self.D0inv), _ptr(r), _ptr(cbuf), cmode,
-                                    self.n, self.lr_rank, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, link, _stream())
+                                    self.n, self.lr_rank, self.L, self.Ly, colour, self.y0 & 1, mg.dcode, nvec, vs, hs, link, _stream())
                     elif self.Dh is not None and nvec == 1 and mg.use_half:
                         lo, hi = self._halo(phi)
                         mg.ctx.call("mg2d_relax_rb_half", _ptr(phi), lo, hi, _ptr(self.Dh), _ptr(self.D0inv_h), _ptr(r),
@@ -716,6 +717,12 @@ def compute_coarse_matrix(lvl_c: Level, lvl_f: Level, lvl_P: Level, quad: int):
     if (mg.lowrank and nf <= 2 and quad == 1 and lvl_P is lvl_f and lvl_c.Ly * lvl_f.block == lvl_f.Ly
             and 2 * lvl_f.block < nc and mg.ctx.lib.mg2d_lowrank_supported(nc, lvl_f.block)):
         lvl_c.hop_factors(lvl_f, P, p_lo, p_hi)
+        # (read now, not at the end of the setup: the next level's near-null relaxation already runs on the factors)
+        if mg.comm is not None:
+            mg.comm.allreduce(mg.status, "max")
+        if int(mg.status[1].item()) != 0:      # a fine hopping block that is not rank one: keep the dense blocks
+            lvl_c.F, lvl_c._lr_AB, lvl_c.lr_rank = None, None, 0
+            mg.status[1] = 0
     if lvl_f.distributed and not lvl_c.distributed:
         # first replicated level: every rank builds its strip of D_c, then the strips are all-gathered
         blk = lvl_f.block

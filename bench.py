@@ -496,9 +496,9 @@ def main():
         t_rb1 = (t_rb1b - t_rb1a) / 2
         if l1.lr_rank and mg.lowrank:
             R1 = l1.lr_rank      # rank-R factors of the 4 hopping blocks: 2 * 4R * n numbers per site instead of 4 n^2
-            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},2> x2 (one red-black GS sweep on the rank-{R1} factors of the pre-multiplied "
+            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},1,2> x2 (one red-black GS sweep on the rank-{R1} factors of the pre-multiplied "
                          f"hopping blocks, level 1)", (8 * R1 * n1 + 3 * n1) * 16.0 * l1.S, t_rb1))
-            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
+            kern.append((f"stencil_rb_lr_kernel<double,{n1},{R1},1,1> x2 (first sweep of a relax call: also forms c = D0^-1 r, level 1)",
                          (8 * R1 * n1 + n1 * n1 + 4 * n1) * 16.0 * l1.S, t_rb1a))
         else:
             kern.append((f"stencil_rb_pm_kernel<double,{n1},1,2> x2 (one red-black GS sweep on pre-multiplied blocks, level 1)",
@@ -550,6 +550,9 @@ def main():
         if top["level"] == 0:       # matrix-free two-colour sweep per vector: 128 B per site and sweep
             by = 128.0 * lt.S * nv * p.null_iters
             kname = "wilson_rb2_kernel<double> (matrix-free sweeps of the 8 near-null candidates, level 0)"
+        elif lt.lr_rank and mg.lowrank:   # batched sweep on the rank-R factors: 4 vectors share one stream of them
+            by = ((8 * lt.lr_rank * lt.n) * (nv // 4 if nv % 4 == 0 else nv) + 3 * lt.n * nv) * 16.0 * lt.S * p.null_iters
+            kname = f"stencil_rb_lr_kernel<double,{lt.n},{lt.lr_rank},4,0> x2 (batched near-null relaxation on the low-rank factors, level {top['level']})"
         else:                       # batched sweep on the dense pre-multiplied blocks: 4 vectors share one stream of M
             by = ((4 * lt.n * lt.n) * (nv // 4 if nv % 4 == 0 else nv) + 3 * lt.n * nv) * 16.0 * lt.S * p.null_iters
             kname = f"stencil_rb_pm_kernel<double,{lt.n},4,0> x2 (batched near-null relaxation, level {top['level']})"

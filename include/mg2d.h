@@ -125,7 +125,7 @@ int mg2d_relax_rb_pm_sweeps(mg2d_ctx*, void* phi, const void* M, const void* D0i
  *   mg2d_hop_factors   A, B [Sc][4*block][nc] from the fine operator Df (n_dof 1 or 2) and the projector P (+ halo rows);
  *                      *status |= 4 when a fine hopping block is not rank one to 1e-13 (the caller then keeps dense blocks)
  *   mg2d_lowrank_pack  F[s][2][n*rank/8][32]: conj(B) and -D0inv A in the lane order of the sweep kernel
- *   mg2d_relax_rb_lr   the red-black half sweep of mg2d_relax_rb_pm (same cmode / link meaning, one vector) streaming
+ *   mg2d_relax_rb_lr   the red-black half sweep of mg2d_relax_rb_pm (same cmode / link / batch meaning) streaming
  *                      2*4*rank*n numbers per site instead of 4*n*n.  (n, rank) in {(16,4), (8,2)}: 8 null vectors over
  *                      4x4 aggregates, 4 over 2x2 (wilson); 16 over 4x4 (laplace). */
 int mg2d_lowrank_supported(int n, int rank);
@@ -135,7 +135,7 @@ int mg2d_lowrank_pack(mg2d_ctx*, void* F, const void* A, const void* B, const vo
                       long long nsites, int dtype, void* stream);
 int mg2d_relax_rb_lr(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* F, const void* D0inv,
                      const void* r, void* cbuf, int cmode, int n, int rank, int Lx, int Ly, int colour, int yoff,
-                     int dtype, const struct mg2d_halo_link* link, void* stream);
+                     int dtype, int nvec, long long vstride, long long hstride, const struct mg2d_halo_link* link, void* stream);
 
 /* The same half sweep for the complex64 preconditioner hierarchy with the operator stored in half precision:
  * Dh / D0invh are __half2 (re,im) arrays in the [s][k][j][i] / [s][j][i] order (built by mg2d_to_half from the complex64

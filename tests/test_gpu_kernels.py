@@ -290,6 +290,15 @@ def test_lowrank_hop_factors_and_sweep(stencil, block, n_null):
         assert rel(out[True], o2.phi) < 1e-11 and rel(out[False], o2.phi) < 1e-11
         assert float((out[True] - out[False]).abs().max()) < 1e-12 * float(out[False].abs().max())
     assert lv.M is not None         # the dense path above rebuilt its blocks lazily
+    # batches of 4 vectors share one stream of the factors (near-null relaxation): equal to one vector at a time, bit for bit
+    for nvec in (4, 8):
+        V = T(crand(rng, nvec, Sc, nc))
+        Vb = V.clone()
+        lv.relax(2, phi=Vb, r=None, smoother="rbgs")
+        for k in range(nvec):
+            one = V[k].clone()
+            lv.relax(2, phi=one, r=None, smoother="rbgs")
+            assert torch.equal(Vb[k], one), (nvec, k)
 
 
 def test_lowrank_not_used_when_fine_hops_are_not_rank_one():
