@@ -381,25 +381,59 @@ extern "C" int mg2d_axpy_ratio2(mg2d_ctx* ctx, void* y, const void* x, void* y2,
 namespace {
 constexpr int GCR_MAXJ = 8;
 
-template <typename T>
+// the projections, specialised on the number of stored directions like gcr_ortho_w_kernel (registers follow NJ; U independent
+// elements per thread keep (NJ+1)*U loads in flight)
+template <typename T, int NJ, int U>
 __global__ void __launch_bounds__(BL_THREADS)
-gcr_dots_kernel(const cplx<T>* __restrict__ W, long long stride, int nj, const cplx<T>* __restrict__ w, long long n,
-                double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
+gcr_dots_nj_kernel(const cplx<T>* __restrict__ W, long long stride, const cplx<T>* __restrict__ w, long long n,
+                   double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ out, XComm* xc) {
+    using C = cplx<T>;
     double red[2 * GCR_MAXJ];
 #pragma unroll
     for (int k = 0; k < 2 * GCR_MAXJ; ++k) red[k] = 0.0;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const cplx<T> b = __ldg(w + e);
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e0 < n; e0 += nthreads * U) {
+        C b[U], a[U][NJ];
 #pragma unroll
-        for (int j = 0; j < GCR_MAXJ; ++j) {
-            if (j < nj) {
-                const cplx<T> a = __ldg(W + (size_t)j * stride + e);
-                red[2 * j] += (double)a.x * b.x + (double)a.y * b.y;
-                red[2 * j + 1] += (double)a.x * b.y - (double)a.y * b.x;
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * nthreads;
+            if (e < n) {
+                b[u] = __ldg(w + e);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) a[u][j] = __ldg(W + (size_t)j * stride + e);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e0 + u * nthreads < n) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    red[2 * j] += (double)a[u][j].x * b[u].x + (double)a[u][j].y * b[u].y;
+                    red[2 * j + 1] += (double)a[u][j].x * b[u].y - (double)a[u][j].y * b[u].x;
+                }
             }
         }
     }
     grid_reduce<2 * GCR_MAXJ, BL_THREADS>(red, partials, counter, out, blockIdx.x, gridDim.x, xc);
+}
+
+template <typename T>
+int launch_dots_nj(mg2d_ctx* ctx, const void* W, long long stride, int nj, const void* w, long long nelem, double* out, cudaStream_t st) {
+    using C = cplx<T>;
+    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
+#define DK(NJ, U) gcr_dots_nj_kernel<T, NJ, U><<<stream_grid(ctx, nelem, U), BL_THREADS, 0, st>>>((const C*)W, stride, (const C*)w, nelem, ctx->partials, ctx->counter, out, xc)
+    switch (nj) {
+        case 1: DK(1, 4); break;
+        case 2: DK(2, 4); break;
+        case 3: DK(3, 2); break;
+        case 4: DK(4, 2); break;
+        case 5: DK(5, 2); break;
+        case 6: DK(6, 1); break;
+        case 7: DK(7, 1); break;
+        default: DK(8, 1); break;
+    }
+#undef DK
+    return mg2d_check_launch(ctx, "mg2d_gcr_dots");
 }
 
 template <typename T>
@@ -622,12 +656,9 @@ extern "C" int mg2d_gcr_dots(mg2d_ctx* ctx, const void* W, long long stride, int
     if (!ctx) return MG2D_EINVAL;
     if (!W || !w || !out || nj < 1 || nj > GCR_MAXJ || nelem < 1) return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_dots: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stream_grid(ctx, nelem);
-    XComm* xc = ctx->xreduce ? ctx->xcomm : nullptr;
-    DISPATCH_T(dtype,
-        (gcr_dots_kernel<double><<<grid, BL_THREADS, 0, st>>>((const double2*)W, stride, nj, (const double2*)w, nelem, ctx->partials, ctx->counter, out, xc)),
-        (gcr_dots_kernel<float><<<grid, BL_THREADS, 0, st>>>((const float2*)W, stride, nj, (const float2*)w, nelem, ctx->partials, ctx->counter, out, xc)),
-        "mg2d_gcr_dots");
+    if (dtype == MG2D_C128) return launch_dots_nj<double>(ctx, W, stride, nj, w, nelem, out, st);
+    if (dtype == MG2D_C64) return launch_dots_nj<float>(ctx, W, stride, nj, w, nelem, out, st);
+    return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_gcr_dots: bad dtype");
 }
 
 extern "C" int mg2d_gcr_ortho(mg2d_ctx* ctx, void* w, void* z, const void* r, const void* W, const void* Z, long long stride, int nj,

@@ -512,7 +512,9 @@ def main():
         t_res = time_kernel(lambda: lv0.restriction(l1.r, a, 1), 10, flush)
         chiral = lv0.phi_null_c is not None          # compacted projector: nc x nf/2 per fine site
         pb = n1 * (1 if chiral else 2)
-        kern.append((f"restrict{'_chiral' if chiral else ''}_kernel<double,2,{n1}> (level 0->1)", ((pb + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
+        rname = ("restrict_chiral_nf2_nc16_blk4_kernel<double>" if (chiral and n1 == 16 and lv0.block == 4)
+                 else f"restrict{'_chiral' if chiral else ''}_kernel<double,2,{n1}>")
+        kern.append((f"{rname} (level 0->1)", ((pb + 2) * 16.0 + n1 * 16.0 / 16) * S0, t_res))
         t_pro = time_kernel(lambda: lv0.prolongation(b_, l1.phi, 1), 10, flush)
         kern.append((f"prolong{'_chiral' if chiral else ''}_kernel<double,2,{n1}> (level 1->0, accumulate)", ((pb + 2 * 2) * 16.0 + n1 * 16.0 / 16) * S0, t_pro))
     barrier()
