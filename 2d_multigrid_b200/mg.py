@@ -972,6 +972,7 @@ class CycleGraph:
         self.graph = None
         self.weights = None
         self.nlaunch = 0
+        self.ptrs = None
         self.enabled = mg.p.smoother != "gs"
 
     def _body(self):
@@ -986,9 +987,13 @@ class CycleGraph:
         if not self.enabled:
             self._body()
             return
+        ptrs = tuple((lv.phi.data_ptr(), lv.r.data_ptr()) for lv in self.mg.LVL)
+        if self.graph is not None and ptrs != self.ptrs:
+            self.graph = None          # a caller rebound phi / r of a level: the captured pointers are stale, capture again
         if self.graph is None:
             # warm-up on a side stream (allocates every lazily created work buffer), then capture
             mg = self.mg
+            self.ptrs = ptrs
             saved = [(lv, lv.phi.clone(), lv.r.clone()) for lv in mg.LVL]
             saved += [(nt, nt.phi.clone(), nt.r.clone()) for row in mg.NTL for nt in row if nt.phi is not None and nt.r is not None]
             s = torch.cuda.Stream()
