@@ -34,6 +34,11 @@ def estimate_critical_mass(U, params_factory, m0: float = 0.0, iters: int = 6, r
             lv.apply_D(Dx, x)
             rq = (torch.vdot(x.reshape(-1), Dx.reshape(-1)) / torch.vdot(x.reshape(-1), x.reshape(-1))).item()
             lam = complex(rq) - m            # eigenvalue of D(0)
+            # how good is the pair?  |D x - rq x| / |x| (the eigen-residual: with it the estimate is off by at most that much
+            # times the condition number of the eigenvector basis) and the change of the estimate in this step
+            res = float(torch.linalg.vector_norm(Dx - rq * x) / torch.linalg.vector_norm(x))
+            estimate_critical_mass.info = {"eig_residual": res, "last_change": abs(lam - hist[-1]) if hist else None,
+                                           "steps": len(hist) + 1}
             hist.append(lam)
             if verbose:
                 print(f"  stage {stage} m={m:+.5f} iters={info['iters']} lambda(D0)~{lam:.6f}")
@@ -43,3 +48,6 @@ def estimate_critical_mass(U, params_factory, m0: float = 0.0, iters: int = 6, r
         gc.collect()
         torch.cuda.empty_cache()
     return -lam.real, hist
+
+
+estimate_critical_mass.info = {}

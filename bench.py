@@ -591,7 +591,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic",
         "config": {"workload": f"wilson{L}_adaptive_mg_near_critical", "L": L, "beta": 6.0, "hbm_gb_in_use": round(torch.cuda.max_memory_allocated() / 1e9, 1), "plaquette": plaq, "mass": mass,
-                   "m_crit_est": mcrit, "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
+                   "m_crit_est": mcrit, "m_crit_quality": getattr(critical.estimate_critical_mass, "info", None), "delta": args.delta, "levels": p.size, "n_dof": p.n_dof, "block": 4, "n_null": 8,
                    "smoother": "rbgs, pre 0, post " + str(p.post), "outer": "fgcr(8)", "tol": TOL, "iters": info["iters"],
                    "executed_iters": info.get("executed_iters"), "n1_reference": ref_n1,
                    "iters_match_n1": (None if ref_n1 is None else ref_n1["iters_match_n1"]),
