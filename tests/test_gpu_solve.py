@@ -351,6 +351,43 @@ def test_error_spectrum_on_device_matches_oracle_history():
     assert lo1 < lo0 and hi1 < hi0           # relaxation damps both bands
 
 
+def test_critical_mass_estimate_against_dense_spectrum():
+    """critical.estimate_critical_mass (shifted inverse iteration with MG-preconditioned FGCR solves, gamma5-symmetric
+    quotient) against the dense spectrum of the oracle's 1152 x 1152 Wilson matrix D(0): D(0) + m becomes singular where m
+    crosses minus the smallest REAL eigenvalue.  The links carry one unit of topological charge (constant flux + noise), which
+    gives D(0) an isolated real mode -- as the large quenched lattices of the bench have, and small ones usually do not."""
+    from importlib import import_module
+    critical = import_module("2d_multigrid_b200.critical")
+    L = 24
+    rng = np.random.default_rng(3)
+    F = 2 * np.pi / (L * L)
+    s = np.arange(L * L)
+    x, y = s % L, s // L
+    th = np.zeros((L * L, 2))
+    th[:, 0] = -F * y
+    th[:, 1] = np.where(y == L - 1, F * L * x, 0.0)
+    th += 0.15 * rng.normal(size=th.shape)
+    U = np.exp(1j * th)
+    po = O.Params(L=L, num_iters=1, block=2, m=0.0, nlevels=1)
+    lv = O.Level()
+    lv.compute_lvl0_matrix(U, po)
+    S = L * L
+    A = np.zeros((2 * S, 2 * S), dtype=complex)
+    e = np.zeros((S, 2), dtype=complex)
+    for col in range(2 * S):
+        e.reshape(-1)[col] = 1.0
+        A[:, col] = lv.apply_D(e, L).reshape(-1)
+        e.reshape(-1)[col] = 0.0
+    ev = np.linalg.eigvals(A)
+    lam_real = np.sort(ev[np.abs(ev.imag) < 1e-9].real)[0]
+    assert 0.0 < lam_real < 0.1
+    factory = lambda m: mg2d.make_params(L, m, nlevels=2, block=2, n_null=4, n_smooth=3, smoother="rbgs", null_iters=40, tol=1e-10)
+    mcrit, hist = critical.estimate_critical_mass(T(U), factory)
+    info = critical.estimate_critical_mass.info
+    assert abs(mcrit + lam_real) < 1e-4, (mcrit, lam_real, info)
+    assert info["last_change"] < 2e-5 and info["quotient"] == "gamma5" and abs(info["imag"]) < 1e-8
+
+
 def test_complex64_and_mixed_precision_solves():
     """complex64 hierarchy (true residual ~1e-6 class) and the mixed-precision solve: complex64 V-cycle inside the
     complex128 FGCR must reach the same 1e-10 TRUE residual (fp64 check) as the all-complex128 solve."""
