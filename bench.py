@@ -280,6 +280,35 @@ def time_kernel(fn, reps, flush=None):
     return tot / reps
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process (and with it its first-touch / pinned host allocations) to the CPUs of the NUMA node the GPU hangs off:
+    with 8 ranks copying their strips at the same time, host buffers on the wrong socket halve the copy bandwidth.
+    Returns the node (or None when the topology cannot be read); never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                                   # 0000:xx:yy.z
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        orig = os.sched_getaffinity(0)
+        allowed = cpus & orig
+        if allowed:
+            bind_to_gpu_numa_node.orig = orig
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,6 +337,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)      # before any pinned allocation: the e2e leg moves 2 x 537 MB through host memory
     comm = dist_mod.init(world, rank, local) if world > 1 else None
     L = args.L
     pk, pk_src = peaks()
@@ -563,6 +593,8 @@ def main():
                                    "note": "whole phase (sweeps + renormalisations) over the algorithmic bytes of its sweeps"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded oracle sample, scaled ----------------------------------
+    if getattr(bind_to_gpu_numa_node, "orig", None):       # the CPU arm gets every core of the host again
+        os.sched_setaffinity(0, bind_to_gpu_numa_node.orig)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -597,7 +629,7 @@ def main():
                    "iters_match_n1": (None if ref_n1 is None else ref_n1["iters_match_n1"]),
                    "final_true_residual": info.get("true_resnorm"), "converged": info["converged"],
                    "setup_s": t_setup, "mcrit_s": t_crit, "cache": "working set >> L2 (126 MB); kernel timings flush L2 with a 256 MiB write",
-                   "parallelism": f"strip{world}"},
+                   "parallelism": f"strip{world}", "numa_node_rank0": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
         "gpu_launches": launches,
