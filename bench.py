@@ -503,6 +503,23 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t.item())
     nbytes = L * L * 2 * 16
+    # one more, instrumented pass (not part of any reported number): where does the end-to-end step spend its time?
+    barrier()
+    t0 = time.perf_counter()
+    r_dev = mg.scatter_field(rhs_host) if comm is not None else rhs_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    xx, _ = mg2d.solve(mg, rhs=r_dev, tol=TOL, outer="gcr", restart=8, use_graph=True, check_every=1)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    if comm is not None:
+        mg.gather_field(xx, x_host)
+    else:
+        x_host.copy_(xx, non_blocking=True)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    e2e_parts = {"h2d_ms": (t1 - t0) * 1e3, "solve_ms": (t2 - t1) * 1e3, "d2h_ms": (t3 - t2) * 1e3}
+    log("e2e parts (rank 0, one extra pass): " + ", ".join(f"{k} {v:.2f}" for k, v in e2e_parts.items()))
 
     log("e2e done; kernel timings")
     # ---- per-kernel rooflines (every rank runs them: strip-level kernels exchange halos; rank 0 reports) -------
@@ -631,7 +648,7 @@ def main():
                    "setup_s": t_setup, "mcrit_s": t_crit, "cache": "working set >> L2 (126 MB); kernel timings flush L2 with a 256 MiB write",
                    "parallelism": f"strip{world}", "numa_node_rank0": numa},
         "clocks": clocks,
-        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+        "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "parts_rank0": e2e_parts},
         "gpu_launches": launches,
         "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s",
                      "frac": dom["frac"], "traffic": traffic, "peak_source": pk_src},
