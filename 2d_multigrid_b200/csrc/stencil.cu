@@ -798,6 +798,87 @@ gs_wavefront_kernel(cplx<T>* phi, const cplx<T>* __restrict__ D, const cplx<T>* 
     }
 }
 
+// The same sweep on a STRIP of rows [y0, y0+Ly) of the global L x Lg lattice (multi-GPU): the anti-diagonal fronts x + y = c are
+// global, every rank updates the part of front c that lies in its rows.  What a front needs from the neighbours
+// (lexicographic order, x outer / y inner, S6/level.h:104-123):
+//   * first local row reads phi(x, y0-1): the value the previous rank produced on front c-1 (NEW), except on rank 0 where it is
+//     the periodic wrap row Lg-1, still OLD when column x starts -> `lo` halo, filled by an exchange before the sweep, and on
+//     ranks > 0 overwritten entry by entry by the previous rank as it goes;
+//   * last local row reads phi(x, y0+Ly): OLD (the next rank updates it one front later, in ITS memory) -> `hi` halo from the
+//     exchange; except on the last rank, where it is row 0 of rank 0, already NEW -> rank 0 stores its row-0 results into the
+//     last rank's `hi` halo.
+// Progress is published through a dedicated halo slot: flag_lo = 1 + last front whose last-row value the previous rank has
+// delivered, flag_hi = 1 + last column rank 0 has delivered (both offset by the sweep count, slot epoch * 4L); a front is
+// entered only when the value it needs has arrived.  One sweep per launch (the caller exchanges OLD rows in between).
+// Latency-bound by construction (2L-1 dependent fronts + a flag hop per front): parity mode, like the single-GPU kernel.
+struct GsStripLinks {
+    HaloSlot* mine; HaloSlot* next; HaloSlot* last;     // the GS progress slots (mine, next rank's, last rank's)
+    void* push_next_lo;                                 // next rank's lo halo (NULL on the last rank)
+    void* push_last_hi;                                 // last rank's hi halo (non-NULL on rank 0 only)
+    int first, is_last;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(ST_THREADS)
+gs_wavefront_strip_kernel(cplx<T>* phi, const cplx<T>* lo, const cplx<T>* hi, const cplx<T>* __restrict__ D,
+                          const cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ r, int L, int Ly, int y0, int Lg,
+                          GsStripLinks a) {
+    using C = cplx<T>;
+    constexpr int G = GroupOf<N>::G;
+    constexpr int GPB = ST_THREADS / G;
+    cg::grid_group grid = cg::this_grid();
+    const int g = threadIdx.x % G, grp = threadIdx.x / G;
+    const int i = g % N, jp = g / N;
+    const long long ngroups = (long long)gridDim.x * GPB;
+    const long long gid = (long long)blockIdx.x * GPB + grp;
+    __shared__ unsigned long long s_base;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) { s_base = a.mine->epoch * 4ull * (unsigned long long)(L + Lg); s_ok = 1; }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    C* push_lo = (C*)a.push_next_lo;
+    C* push_hi = (C*)a.push_last_hi;
+    for (int c = y0; c <= y0 + Ly - 1 + L - 1; ++c) {
+        const int x0 = max(0, c - (y0 + Ly - 1)), x1 = min(c - y0, L - 1);     // my sites of front c: x in [x0, x1], y = c - x
+        const int cnt = x1 - x0 + 1;
+        const bool has_first = (c - y0 <= L - 1);              // site (c - y0, y0) exists
+        const bool has_last = (c - (y0 + Ly - 1) >= 0);        // site (c - (y0+Ly-1), y0+Ly-1) exists
+        if (threadIdx.x == 0) {
+            bool ok = true;
+            if (has_first && !a.first) ok = spin_until(&a.mine->flag_lo, base + (unsigned long long)c);
+            if (ok && has_last && a.is_last)       // (one rank: it is its own "rank 0" and has delivered column x on front x)
+                ok = spin_until(&a.mine->flag_hi, base + (unsigned long long)(c - (y0 + Ly - 1)) + 1ull);
+            if (!ok) { s_ok = 0; atomicExch(&a.mine->error, 1ull); }
+        }
+        __syncthreads();
+        const long long rounds = (cnt + ngroups - 1) / ngroups;
+        for (long long rd = 0; rd < rounds; ++rd) {
+            long long idx = rd * ngroups + gid;
+            const bool active = idx < cnt;
+            if (!active) idx = cnt - 1;
+            const int x = x0 + (int)idx, yl = c - x - y0;                      // local row
+            const size_t s = (size_t)yl * L + x;
+            C acc = stencil_row<T, N, G, 1, true>(D + s * 5 * N * N, phi, lo, hi, x, yl, L, Ly, g);
+            if (r) acc = csub(acc, __ldg(r + s * N + i));
+            C o = apply_minus_inv<T, N, G>(Dinv + s * N * N, acc, g);
+            if (active && jp == 0) {
+                __stcg(phi + s * N + i, o);
+                if (push_lo && yl == Ly - 1) push_lo[(size_t)x * N + i] = o;
+                if (push_hi && yl == 0) push_hi[(size_t)x * N + i] = o;
+            }
+            if ((push_lo && yl == Ly - 1) || (push_hi && yl == 0)) __threadfence_system();
+        }
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            __threadfence_system();
+            if (push_lo && has_last) st_relaxed_sys(&a.next->flag_lo, base + (unsigned long long)c + 1ull);
+            if (push_hi && has_first) st_relaxed_sys(&a.last->flag_hi, base + (unsigned long long)c + 1ull);   // y0 = 0: c = column
+        }
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.mine->epoch = a.mine->epoch + 1ull;
+}
+
 // D0inv[s] = inverse(D[s][0]); one warp per site, Gauss-Jordan with partial pivoting in shared memory
 template <typename T, int N>
 __global__ void block_inverse_kernel(cplx<T>* __restrict__ Dinv, const cplx<T>* __restrict__ D, long long S) {
@@ -913,6 +994,27 @@ int launch_gs(mg2d_ctx* ctx, void* phi, const void* D, const void* Dinv, const v
     e = cudaLaunchCooperativeKernel((const void*)gs_wavefront_kernel<T, N>, dim3(grid), dim3(ST_THREADS), args, 0, st);
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "mg2d_relax_gs: %s", cudaGetErrorString(e)); return MG2D_ECUDA; }
     return mg2d_check_launch(ctx, "mg2d_relax_gs");
+}
+
+template <typename T, int N>
+int launch_gs_strip(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const void* D, const void* Dinv, const void* r,
+                    int L, int Ly, int y0, int Lg, GsStripLinks a, cudaStream_t st) {
+    using C = cplx<T>;
+    constexpr int GPB = ST_THREADS / GroupOf<N>::G;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_wavefront_strip_kernel<T, N>, ST_THREADS, 0);
+    if (e != cudaSuccess || per_sm < 1) return mg2d_fail(ctx, MG2D_ECUDA, "mg2d_relax_gs_strip: occupancy query failed");
+    const int front = L < Ly ? L : Ly;
+    long long need = ((long long)front + GPB - 1) / GPB;
+    long long cap = (long long)per_sm * ctx->num_sms;
+    int grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    C* phi_ = (C*)phi; const C* lo_ = (const C*)lo; const C* hi_ = (const C*)hi; const C* D_ = (const C*)D;
+    const C* Dinv_ = (const C*)Dinv; const C* r_ = (const C*)r;
+    void* args[] = {&phi_, &lo_, &hi_, &D_, &Dinv_, &r_, &L, &Ly, &y0, &Lg, &a};
+    e = cudaLaunchCooperativeKernel((const void*)gs_wavefront_strip_kernel<T, N>, dim3(grid), dim3(ST_THREADS), args, 0, st);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "mg2d_relax_gs_strip: %s", cudaGetErrorString(e)); return MG2D_ECUDA; }
+    return mg2d_check_launch(ctx, "mg2d_relax_gs_strip");
 }
 
 template <typename T>
@@ -1284,4 +1386,23 @@ extern "C" int mg2d_lowrank_pack(mg2d_ctx* ctx, void* F, const void* A, const vo
 #undef CALL_D
 #undef CALL_F
     return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_lowrank_pack: (n, rank) must be (16,4) or (8,2)");
+}
+
+extern "C" int mg2d_relax_gs_strip(mg2d_ctx* ctx, void* phi, const void* phi_lo, const void* phi_hi, const void* D, const void* D0inv,
+                                   const void* r, int n, int Lx, int Ly, int y0, int Lglobal, int dtype, void* slot_mine,
+                                   void* slot_next, void* slot_last, void* push_next_lo, void* push_last_hi, int first_rank,
+                                   int last_rank, void* stream) {
+    if (!ctx) return MG2D_EINVAL;
+    if (!phi || !phi_lo || !phi_hi || !D || !D0inv || Lx < 2 || Ly < 1 || y0 < 0 || y0 + Ly > Lglobal || !slot_mine || !slot_next || !slot_last)
+        return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_gs_strip: bad argument");
+    GsStripLinks a;
+    a.mine = (HaloSlot*)slot_mine; a.next = (HaloSlot*)slot_next; a.last = (HaloSlot*)slot_last;
+    a.push_next_lo = push_next_lo; a.push_last_hi = push_last_hi; a.first = first_rank; a.is_last = last_rank;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CASE(TT, N) case N: return launch_gs_strip<TT, N>(ctx, phi, phi_lo, phi_hi, D, D0inv, r, Lx, Ly, y0, Lglobal, a, st)
+    if (dtype == MG2D_C128) { switch (n) { CASE(double, 1); CASE(double, 2); CASE(double, 4); CASE(double, 8); CASE(double, 16); CASE(double, 32); default: break; } }
+    else if (dtype == MG2D_C64) { switch (n) { CASE(float, 1); CASE(float, 2); CASE(float, 4); CASE(float, 8); CASE(float, 16); CASE(float, 32); default: break; } }
+    else return mg2d_fail(ctx, MG2D_EINVAL, "mg2d_relax_gs_strip: bad dtype");
+#undef CASE
+    return mg2d_fail(ctx, MG2D_EUNSUPPORTED, "mg2d_relax_gs_strip: n_dof must be one of 1,2,4,8,16,32");
 }

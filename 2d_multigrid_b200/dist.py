@@ -165,6 +165,21 @@ class Comm:
                         {"nowait": 0, "nopush": 0}.get(LINK_DEBUG, 1))
         return link, me + e["lo"][rd], me + e["hi"][rd]
 
+    def gs_links(self, t, Lx, width, key):
+        """Pointers for the strip lexicographic Gauss-Seidel sweep (mg2d_relax_gs_strip) on the field whose halo buffers belong to
+        `key` (the key of the preceding exchange_rows): progress slots (mine, next rank's, last rank's), the next rank's lo
+        buffer and the last rank's hi buffer."""
+        st = self.p2p
+        row = Lx * width * t.element_size()
+        e = self._entry(key, 1, row)
+        gs = self._entry(("gs",) + tuple(key), 1, 16)
+        b = st["base"]
+        last = self.world - 1
+        return {"slot_mine": b[self.rank] + gs["slot"], "slot_next": b[self.next] + gs["slot"], "slot_last": b[last] + gs["slot"],
+                "push_next_lo": None if self.rank == last else b[self.next] + e["lo"][0],
+                "push_last_hi": (b[last] + e["hi"][0]) if self.rank == 0 else None,
+                "first": int(self.rank == 0), "last": int(self.rank == last)}
+
     def check_errors(self):
         """Raise if any exchange / reduction of this rank timed out waiting for a peer (synchronises)."""
         if self.p2p is None:

@@ -298,9 +298,22 @@ class Level:
         vs = self.S * self.n
         if num_iter <= 0:
             return
-        if smoother == "gs":
-            if self.distributed:
-                raise MG2DError("lexicographic Gauss-Seidel is sequential across strips: use 'rbgs', 'jacobi' or 'mr' on multi-GPU levels")
+        if smoother == "gs" and self.distributed:
+            # the reference's own smoother on strips: global anti-diagonal fronts, one flag hop per front (parity mode)
+            if mg.comm.p2p is None:
+                raise MG2DError("lexicographic Gauss-Seidel on strips needs the peer-to-peer halo path (MG2D_HALO=p2p)")
+            self._ensure_D0inv()
+            key = (self.lvl, self.n, 1, 1)
+            for v in range(nvec):
+                ph = phi if nvec == 1 else phi[v]
+                rv = None if r is None else (r if nvec == 1 else r[v])
+                for _ in range(num_iter):
+                    lo, hi = self._halo(ph)                     # the neighbours' OLD boundary rows
+                    g = mg.comm.gs_links(ph, self.L, self.n, key)
+                    mg.ctx.call("mg2d_relax_gs_strip", _ptr(ph), lo, hi, _ptr(self.D), _ptr(self.D0inv), _ptr(rv), self.n, self.L,
+                                self.Ly, self.y0, self.L, mg.dcode, g["slot_mine"], g["slot_next"], g["slot_last"],
+                                g["push_next_lo"], g["push_last_hi"], g["first"], g["last"], _stream())
+        elif smoother == "gs":
             self._ensure_D0inv()
             mg.ctx.call("mg2d_relax_gs", _ptr(phi), _ptr(self.D), _ptr(self.D0inv), _ptr(r), self.n, self.L,
                         num_iter, mg.dcode, nvec, vs, _stream())

@@ -81,6 +81,16 @@ int mg2d_relax_jacobi(mg2d_ctx*, void* out, const void* in, const void* in_lo, c
  * periodic lattice on one GPU (Ly == Lx).  r == NULL means r = 0 (near-null relaxation, S6/level.h:196-198). */
 int mg2d_relax_gs(mg2d_ctx*, void* phi, const void* D, const void* D0inv, const void* r, int n, int L,
                   int num_iter, int dtype, int nvec, long long vstride, void* stream);
+/* One lexicographic Gauss-Seidel sweep (same order: x outer, y inner over the GLOBAL lattice) on the strip of rows [y0, y0+Ly) of an
+ * Lx x Lglobal lattice: global anti-diagonal fronts, every rank updates its part of a front once the value it needs from the
+ * previous rank (first local row; new) has arrived.  phi_lo / phi_hi: this rank's halo buffers holding the neighbours' OLD
+ * boundary rows (mg2d_halo_exchange before every sweep); push_next_lo: the next rank's lo buffer (NULL on the last rank);
+ * push_last_hi: the last rank's hi buffer (rank 0 only: its row 0 is the periodic upper neighbour of the last row);
+ * slot_*: 64-byte progress slots of this rank, the next and the last one (zeroed, peer-mapped).  Parity mode: 2L-1 dependent
+ * fronts and one flag hop per front. */
+int mg2d_relax_gs_strip(mg2d_ctx*, void* phi, const void* phi_lo, const void* phi_hi, const void* D, const void* D0inv,
+                        const void* r, int n, int Lx, int Ly, int y0, int Lglobal, int dtype, void* slot_mine, void* slot_next,
+                        void* slot_last, void* push_next_lo, void* push_last_hi, int first_rank, int last_rank, void* stream);
 
 /* Level::f_relax update rule in red-black (two-colour) ordering, one half sweep IN PLACE: the sites with
  * (x + y + yoff) % 2 == colour are updated from the other colour (parallel stand-in for the sequential

@@ -101,6 +101,82 @@ def test_ntl_cycle_on_strips_with_replicated_copy_levels():
     ref.close(); dmg.close()
 
 
+def _gs_problem(L, dev):
+    U = mg2d.gauge.quenched_links_device(L, 6.0, sweeps=20, seed=1234, device=dev)
+    p = mg2d.make_params(L, 0.02, nlevels=2, block=2, n_null=2, n_smooth=2, smoother="gs", null_iters=16, tol=1e-10, max_iters=200)
+    rhs = torch.zeros((L * L, 2), dtype=torch.complex128, device=f"cuda:{dev}")
+    rhs[L // 2 + (L // 2) * L, 0] = 1.0
+    return U, p, rhs
+
+
+def test_lexicographic_gs_on_a_strip_with_self_neighbour():
+    """The reference's own smoother (gs_flag = 1, S6/level.h:100-128) through the strip kernel mg2d_relax_gs_strip with the rank
+    as its own neighbour: global fronts, the periodic upper neighbour of the last row delivered through the halo buffer and its
+    progress flag.  One sweep is bit-identical to the single-GPU wavefront kernel; the whole solve needs the same iterations."""
+    L = 64
+    U, p, rhs = _gs_problem(L, 0)
+    ref = mg2d.setup(U, p, init="device")
+    comm = dmod.Comm.single(mg2d.Context(0), torch.device("cuda", 0))
+    dmg = dmod.setup(U, p, comm, min_rows=8)
+    assert [d for d, _ in dmg.plan] == [True, True, True]
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    for lvl in (0, 1):
+        a, b = ref.LVL[lvl], dmg.LVL[lvl]
+        assert float((a.D - b.D).abs().max()) < 1e-12 * float(a.D.abs().max())
+        b.D.copy_(a.D); b.D0inv = None; a.D0inv = None
+        v = torch.randn((a.S, a.n, 2), generator=g, dtype=torch.float64, device="cuda")
+        v = torch.view_as_complex(v).contiguous()
+        rr = torch.view_as_complex(torch.randn((a.S, a.n, 2), generator=g, dtype=torch.float64, device="cuda")).contiguous()
+        va, vb = v.clone(), v.clone()
+        a.relax(2, phi=va, r=rr, smoother="gs")
+        b.relax(2, phi=vb, r=rr, smoother="gs")
+        assert torch.equal(va, vb), lvl
+    ref2 = mg2d.setup(U, p, init="device")
+    x_ref, i_ref = mg2d.solve(ref2, rhs=rhs, tol=1e-10)
+    dmg2 = dmod.setup(U, p, comm, min_rows=8)
+    x, info = mg2d.solve(dmg2, rhs=rhs, tol=1e-10)
+    assert info["converged"] and info["iters"] == i_ref["iters"]
+    assert float((x - x_ref).abs().max() / x_ref.abs().max()) < 1e-9
+    assert comm.p2p_errors() == 0
+
+
+def _gs_worker(rank, world, port, L, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    comm = dmod.init(world, rank, rank)
+    U, p, rhs = _gs_problem(L, rank)
+    res = {}
+    if rank == 0:
+        ref = mg2d.setup(U, p, init="device")
+        x_ref, i_ref = mg2d.solve(ref, rhs=rhs, tol=1e-10)
+        x_ref = x_ref.clone()
+    dmg = dmod.setup(U, p, comm, min_rows=8)
+    x, info = mg2d.solve(dmg, rhs=dmg.scatter_field(rhs), tol=1e-10)
+    if rank == 0:
+        lv0 = dmg.LVL[0]
+        dx = float((x - x_ref[lv0.y0 * L:(lv0.y0 + lv0.Ly) * L]).abs().max() / x_ref.abs().max())
+        res = dict(dx=dx, iters=info["iters"], ref_iters=i_ref["iters"], conv=info["converged"], errors=comm.p2p_errors(),
+                   plan=[d for d, _ in dmg.plan])
+        out.put(res)
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_lexicographic_gs_on_two_ranks_equals_single_gpu():
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_gs_worker, args=(r, 2, 29537, 64, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    r = out.get(timeout=600)
+    for pr in procs:
+        pr.join(timeout=120)
+    assert all(r["plan"]) and r["conv"] and r["iters"] == r["ref_iters"] and r["dx"] < 1e-9 and r["errors"] == 0, r
+
+
 def _worker(rank, world, port, L, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
