@@ -1081,9 +1081,10 @@ int launch_rb_pm(mg2d_ctx* ctx, void* phi, const void* lo, const void* hi, const
     long long cap = (long long)ctx->num_sms * 32;
     const int gx = (int)(nsteps < cap ? nsteps : cap);
     const HaloLinkDev ld = make_link(link);
-    // resident CTAs per SM are capped through (unused) dynamic shared memory: measured on B200 (ncu, 16-dof blocks), the sweep
-    // is FASTER with 5 CTAs of 256 threads per SM than with the 6 the register count would allow (90 vs 99 us for 0.56 GB):
-    // more concurrent 512-byte streams per SM only thrash DRAM pages
+    // resident CTAs per SM are capped at 5 through (unused) dynamic shared memory.  Measured on B200 (tools/link_probe.py, 16-dof
+    // blocks): a halo-linked half sweep on a 256 x 32 strip takes 18.2 us with 5 CTAs of 256 threads per SM and 20.4 us with the 6
+    // the register count would allow; whole-lattice sweeps do not care (15.0 us / 92 us either way).  MG2D_PM_CTAS overrides.
+    // (Also measured and rejected: programmatic dependent launch for this kernel -- -0.5 us on a whole lattice, +2 us on strips.)
     static int pm_ctas = -1;
     if (pm_ctas < 0) { const char* e = getenv("MG2D_PM_CTAS"); pm_ctas = e ? atoi(e) : 5; if (pm_ctas < 1 || pm_ctas > 8) pm_ctas = 5; }
     const size_t dsm = (N >= 8) ? (size_t)(200 * 1024 / pm_ctas / 1024) * 1024 - 2048 : 0;     // <= 48 KB for >= 5 CTAs (no attribute needed)
