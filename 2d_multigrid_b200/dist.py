@@ -91,6 +91,15 @@ class Comm:
     # ---- peer-to-peer path: CUDA-IPC slabs ---------------------------------------------------------------------
     def enable_p2p(self, ctx, device, slab_bytes: int = SLAB_BYTES):
         """Allocate this rank's slab, trade IPC handles, map every peer's slab, build the reduction descriptor."""
+        if self.world > 1:
+            # CUDA IPC maps memory between processes of ONE node: refuse clearly instead of failing inside cudaIpcOpenMemHandle
+            import socket
+            hosts = [None] * self.world
+            dist.all_gather_object(hosts, socket.gethostname(), group=self.group)
+            if len(set(hosts)) != 1:
+                from ._lib import MG2DError
+                raise MG2DError(f"the peer-to-peer halo path needs all ranks on one node (got {sorted(set(hosts))}); "
+                                "use MG2D_HALO=nccl for strips across nodes")
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
         ctx.call("mg2d_ipc_alloc", slab_bytes, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))

@@ -1,6 +1,6 @@
 """N>1 host logic on CPU: world_size-2 gloo processes exercise the strip plan, the halo exchange ordering (with
 2 ranks both neighbours are the same peer), all-reduce and the strip all-gather used for coarse-level
-agglomeration.  The CUDA side of the same code path is covered by tools/dist_check.py on 2 B200s."""
+agglomeration.  The CUDA side of the same code path is covered by tests/test_gpu_dist.py (self-neighbour on one GPU, 2 ranks when two are visible)."""
 import os
 import socket
 
