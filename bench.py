@@ -112,8 +112,10 @@ def workload_params(mg2d, L, mass, **kw):
 
 def post_sweeps(nlevels):
     """Cycle shape measured fastest at 4096^2 (tools/tune.py): no pre-smoothing, 4 red-black sweeps on the fine lattice,
-    2 on level 1 (whose 16x16-block operator dominates the traffic of a cycle), 8 on the cheap deeper levels."""
-    return ([4, 2] + [8] * nlevels)[:nlevels + 1]
+    2 on level 1 (whose operator dominates the traffic of a cycle), 6 on level 2, 4 on the small levels below (round 2: with
+    8/8/8 there the iteration count is the same 21 -- the coarse levels were over-smoothed; 5 or fewer on level 2, 2 on the
+    small ones, or 3 on the fine lattice cost an iteration or leave no margin to the tolerance)."""
+    return ([4, 2, 6] + [4] * nlevels)[:nlevels + 1]
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 U = mg2d.gauge.quenched_links_device(L, 6.0, sweeps=60, seed=1234)
 mcrit = float(os.environ["MG2D_MCRIT"]) if "MG2D_MCRIT" in os.environ else None
 if mcrit is None:
-    mcrit, _ = critical.estimate_critical_mass(U, lambda m: bench.workload_params(mg2d, L, m), iters=4, refine=3)
+    mcrit, _ = critical.estimate_critical_mass(U, lambda m: bench.workload_params(mg2d, L, m))
 p = bench.workload_params(mg2d, L, mcrit + 1e-3)
 mg = mg2d.setup(U, p, init="device")
 rhs = torch.zeros((L * L, 2), dtype=torch.complex128, device=dev); rhs[L // 2 + (L // 2) * L, 0] = 1.0
@@ -25,13 +25,17 @@ def run(pre, post, mixed, restart=8):
     if mixed:   # the shadow was created with the default counts on first use: re-apply and re-run
         m = mg.info["single"]; m.p.pre, m.p.post = list(pre), list(post); m.info.pop("precond_graph", None)
         x, info = mg2d.solve(mg, **kw)
-    torch.cuda.synchronize(); t0 = time.time()
-    x, info = mg2d.solve(mg, **kw)
-    torch.cuda.synchronize(); return info, (time.time() - t0) * 1e3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(3):
+        x, info = mg2d.solve(mg, **kw)
+    e1.record(); torch.cuda.synchronize(); return info, e0.elapsed_time(e1) / 3
 def configs():
     z = [0] * (nl + 1)
-    for post in ([4, 2, 8, 8, 8], [4, 3, 8, 8, 8], [4, 4, 8, 8, 8], [3, 3, 8, 8, 8], [3, 2, 8, 8, 8], [2, 2, 8, 8, 8], [4, 2, 6, 8, 8],
-                 [4, 3, 6, 8, 8], [4, 3, 4, 8, 8], [4, 2, 4, 8, 8], [4, 4, 4, 8, 8], [6, 3, 8, 8, 8], [4, 3, 8, 4, 8]):
+    shapes = os.environ.get("MG2D_TUNE_SHAPES")
+    shapes = ([[int(t) for t in sh.split(",")] for sh in shapes.split(";")] if shapes else
+              [[4, 2, 8, 8, 8], [4, 2, 8, 4, 8], [4, 2, 8, 4, 4], [4, 2, 8, 8, 4], [4, 2, 6, 4, 4], [4, 2, 8, 6, 6], [3, 2, 8, 8, 8], [4, 3, 8, 8, 8]])
+    for post in shapes:
         yield f"post {post[:nl + 1]}", z, post[:nl + 1]
 
 
