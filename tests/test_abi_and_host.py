@@ -104,3 +104,50 @@ def test_error_spectrum_diagnostics():
     assert float(spec.max()) < 1e-9
     lo, hi = mg2d.diagnostics.mode_amplitudes(phi, phi_star, L)
     assert hi > 100 and lo < 1e-9        # (3,5): ky > L/4 -> a high-frequency mode
+
+
+def test_gamma5_quotient_is_second_order():
+    """critical._quotients (host logic of the critical-mass estimate): D is gamma5-hermitian, so for a right eigenvector x the
+    left one is gamma5 x and <g5 x, D x>/<g5 x, x> has a second-order error in a perturbation of x where the plain Rayleigh
+    quotient of this non-normal matrix has a first-order one.  Dense 8^2 Wilson matrix of the oracle, links with one unit of
+    flux (an isolated real mode)."""
+    import numpy as np
+    import torch
+    from importlib import import_module
+    from oracle import mg_oracle as O
+    critical = import_module("2d_multigrid_b200.critical")
+    L = 8
+    rng = np.random.default_rng(1)
+    F = 2 * np.pi / (L * L)
+    s = np.arange(L * L)
+    x, y = s % L, s // L
+    th = np.zeros((L * L, 2))
+    th[:, 0] = -F * y
+    th[:, 1] = np.where(y == L - 1, F * L * x, 0.0)
+    th += 0.1 * rng.normal(size=th.shape)
+    lv = O.Level()
+    lv.compute_lvl0_matrix(np.exp(1j * th), O.Params(L=L, num_iters=1, block=2, m=0.0, nlevels=1))
+    S = L * L
+    A = np.zeros((2 * S, 2 * S), dtype=complex)
+    e = np.zeros((S, 2), dtype=complex)
+    for col in range(2 * S):
+        e.reshape(-1)[col] = 1.0
+        A[:, col] = lv.apply_D(e, L).reshape(-1)
+        e.reshape(-1)[col] = 0.0
+    g5 = np.tile([1.0, -1.0], S)
+    assert np.abs(g5[:, None] * A * g5[None, :] - A.conj().T).max() < 1e-13          # gamma5 D gamma5 = D^dagger
+    w, V = np.linalg.eig(A)
+    k = np.argmin(np.where(np.abs(w.imag) < 1e-9, w.real, np.inf))
+    lam, v = w[k].real, V[:, k]
+    errs = []
+    d = (rng.normal(size=2 * S) + 1j * rng.normal(size=2 * S)) / np.sqrt(2 * S)
+    for eps in (1e-2, 1e-3):
+        xp = v + eps * d
+        xt = torch.as_tensor(xp.reshape(S, 2))
+        Dx = torch.as_tensor((A @ xp).reshape(S, 2))
+        q5, rq = critical._quotients(xt, Dx, True)
+        errs.append((abs(q5 - lam), abs(rq - lam)))
+    assert errs[1][0] < 2e-2 * errs[0][0] + 1e-14        # x10 smaller perturbation -> ~x100 smaller error
+    assert errs[1][0] < 0.1 * errs[1][1]                  # and far better than the plain Rayleigh quotient
+    q5, rq = critical._quotients(torch.as_tensor(v.reshape(S, 2)), torch.as_tensor((A @ v).reshape(S, 2)), True)
+    assert abs(q5 - lam) < 1e-12
